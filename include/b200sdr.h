@@ -1,0 +1,220 @@
+/*
+ * b200sdr.h -- C ABI of libb200sdr: the B200-native IQ sample-processing path that
+ * replaces "what happens to the sample buffer" in vpecanins/stm32f7-rtlsdr.
+ *
+ * Reference interfaces this boundary stands in for (paths relative to the reference tree;
+ * RTL/ = Middlewares/ST/STM32_USB_Host_Library/Class/RTLSDR/, USBH/ = .../Core/):
+ *
+ *   - The class plug-in slot `USBH_ClassTypeDef.BgndProcess` (USBH/Inc/usbh_def.h:436-447),
+ *     implemented by `USBH_RTLSDR_Process` (RTL/Src/usbh_rtlsdr.c:1058-1101): once the
+ *     bulk-IN URB is done the FSM sits in RTLSDR_XFER_COMPLETE (:1094-1097) with
+ *     `CommItf.buff[0 .. buffSize)` (RTL/Inc/usbh_rtlsdr.h:165-173) holding u8 interleaved
+ *     I,Q,I,Q...  `process_samples()` below is the consumer the author sketched in the
+ *     commented-out poll at src/main.c:76-79.
+ *   - Status codes are `USBH_StatusTypeDef` (USBH/Inc/usbh_def.h:301-310) by value.
+ *   - The buffer rule "all buffers must have a length that is a multiple of 4 bytes"
+ *     (RTL/Inc/usbh_rtlsdr.h:256-261; word-granular FIFO copy `USB_ReadPacket`,
+ *     HAL_Driver/Src/stm32f7xx_ll_usb.c:792-803) is kept: `len % 4 != 0` is NOT_SUPPORTED.
+ *
+ * Everything here is plain C: pointers and sizes, no C++/torch types.  All device work is
+ * hand-written CUDA for sm_100a inside the library; there is no CPU fallback -- if no
+ * CUDA device is usable `b200sdr_create` fails with B200SDR_FAIL.
+ */
+#ifndef B200SDR_H
+#define B200SDR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200SDR_API __attribute__((visibility("default")))
+#else
+#define B200SDR_API
+#endif
+
+/* ---- status: numerically identical to USBH_StatusTypeDef (USBH/Inc/usbh_def.h:301-310) ---- */
+#define B200SDR_OK                  0 /* USBH_OK */
+#define B200SDR_BUSY                1 /* USBH_BUSY: ring full / result not ready -- call again */
+#define B200SDR_FAIL                2 /* USBH_FAIL: CUDA error or bad handle */
+#define B200SDR_NOT_SUPPORTED       3 /* USBH_NOT_SUPPORTED: bad configuration / bad length */
+#define B200SDR_UNRECOVERED_ERROR   4 /* USBH_UNRECOVERED_ERROR */
+
+/* ---- processing chains (bit mask) ---- */
+#define B200SDR_CHAIN_SPECTRUM 1u /* u8 -> window -> 1024-pt FFT -> |X|^2 -> average      */
+#define B200SDR_CHAIN_WBFM     2u /* u8 -> /10 polyphase FIR -> discriminator -> de-emph -> /5 -> 48 kHz */
+#define B200SDR_CHAIN_AM       4u /* u8 -> /20 -> /10 -> envelope -> DC block -> x2//3 -> 8 kHz */
+
+#define B200SDR_WINDOW_RECT     0u
+#define B200SDR_WINDOW_HANN     1u /* periodic: w[n] = 0.5 - 0.5 cos(2 pi n / N)           */
+#define B200SDR_WINDOW_BLACKMAN 2u /* periodic: 0.42 - 0.5 cos(2 pi n/N) + 0.08 cos(4 pi n/N) */
+
+#define B200SDR_AVG_MEAN 0u /* P[k] = (1/F) sum_m |X_m[k]|^2                              */
+#define B200SDR_AVG_EMA  1u /* P <- (1-beta) P + beta |X_m|^2 per frame, P starts at 0    */
+
+#define B200SDR_NFFT 1024u
+#define B200SDR_HOP  512u
+
+/* fixed DSP parameters (frozen in oracle/golden.c) */
+#define B200SDR_FS            2400000.0
+#define B200SDR_FM_DECIM1     10u
+#define B200SDR_FM_TAPS1      80u
+#define B200SDR_FM_DECIM2     5u
+#define B200SDR_FM_TAPS2      50u
+#define B200SDR_AM_DECIM1     20u
+#define B200SDR_AM_TAPS1      80u
+#define B200SDR_AM_DECIM2     10u
+#define B200SDR_AM_TAPS2      200u
+#define B200SDR_AM_UP3        2u
+#define B200SDR_AM_DECIM3     3u
+#define B200SDR_AM_TAPS3      48u
+
+/* tap-set selectors for b200sdr_get_taps */
+#define B200SDR_TAPS_FM1 0u
+#define B200SDR_TAPS_FM2 1u
+#define B200SDR_TAPS_AM1 2u
+#define B200SDR_TAPS_AM2 3u
+#define B200SDR_TAPS_AM3 4u
+
+typedef struct b200sdr_ctx b200sdr_ctx;
+
+typedef struct b200sdr_config {
+    uint32_t struct_size;   /* sizeof(b200sdr_config), for ABI evolution                      */
+    int32_t  device;        /* CUDA device ordinal                                            */
+    uint32_t chains;        /* B200SDR_CHAIN_* mask run by process_samples()                  */
+    uint32_t window;        /* B200SDR_WINDOW_*                                               */
+    uint32_t avg_mode;      /* B200SDR_AVG_*                                                  */
+    float    ema_beta;      /* used when avg_mode == EMA                                      */
+    uint32_t ring_slots;    /* pinned host ring: number of slots (>= 2)                       */
+    uint32_t slot_bytes;    /* bytes per slot = largest `len` process_samples accepts.
+                               Reference live value 512 (usbh_rtlsdr.c:230); BASELINE block
+                               262144 = DEFAULT_BUF_LENGTH (usbh_rtlsdr.h:277-278).            */
+    uint32_t audio_capacity;/* streaming audio FIFO capacity in float samples per chain       */
+    uint32_t reserved[7];
+} b200sdr_config;
+
+/* Fill *cfg with defaults: device 0, all chains, Hann, mean, 8 slots of 262144 bytes. */
+B200SDR_API void b200sdr_default_config(b200sdr_config *cfg);
+
+/* Create/destroy: the analogue of the class Init/DeInit slots
+ * (USBH_RTLSDR_InterfaceInit / InterfaceDeInit, RTL/Src/usbh_rtlsdr.c:163-260, :621-641),
+ * which malloc/free the handle and set up the sample buffer descriptor. */
+B200SDR_API int32_t b200sdr_create(const b200sdr_config *cfg, b200sdr_ctx **out_ctx);
+B200SDR_API int32_t b200sdr_destroy(b200sdr_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Streaming path.  THE drop-in entry point: called when a buffer is complete, i.e. where the
+ * reference FSM reaches RTLSDR_XFER_COMPLETE (usbh_rtlsdr.c:1094-1097).
+ *   iq  : host pointer, u8 interleaved I,Q (owned by the caller)
+ *   len : bytes; must be a multiple of 4 and <= cfg.slot_bytes
+ *   ctx : the b200sdr_ctx* (void* so the firmware-side prototype needs no extra header)
+ * The block is copied into the next pinned ring slot (so the caller may reuse `iq` on
+ * return, like the reference re-arms the same buffer at once), then an async H2D copy on the
+ * copy stream and the enabled chains on the compute stream are enqueued.  Filter history,
+ * FFT overlap, discriminator / IIR state are carried in ctx from call to call, so a stream
+ * cut into blocks at any 4-byte boundaries yields exactly the result of one long block.
+ * Returns B200SDR_BUSY when every ring slot is still in flight (call again).
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t process_samples(const uint8_t *iq, uint32_t len, void *ctx);
+
+/* Zero-copy variant of the above: get the next free pinned slot to fill in place
+ * (what `CommItf.buff` is to the USB core), then commit `len` bytes of it. */
+B200SDR_API int32_t b200sdr_ring_acquire(b200sdr_ctx *ctx, uint8_t **slot, uint32_t *slot_bytes);
+B200SDR_API int32_t b200sdr_ring_commit(b200sdr_ctx *ctx, uint32_t len);
+
+/* Block until everything enqueued so far has finished on the device. */
+B200SDR_API int32_t b200sdr_sync(b200sdr_ctx *ctx);
+/* Forget all carried state (new capture). */
+B200SDR_API int32_t b200sdr_reset(b200sdr_ctx *ctx);
+
+/* Current averaged power spectrum, 1024 floats in FFT order (k = 0 is DC, k = 512 is -fs/2).
+ * Units: (u8 counts)^2, no normalisation.  *n_frames (optional) = frames averaged so far. */
+B200SDR_API int32_t b200sdr_get_spectrum(b200sdr_ctx *ctx, float *out1024, uint64_t *n_frames);
+/* Pop up to `capacity` demodulated audio samples of one chain (WBFM: 48 kHz, AM: 8 kHz). */
+B200SDR_API int32_t b200sdr_get_audio(b200sdr_ctx *ctx, uint32_t chain, float *out, uint32_t capacity,
+                                      uint32_t *n_out);
+/* Bytes ingested so far / ring overruns (BUSY returns) -- the ingest counters the reference
+ * only prints ("Xfer complete %d B, %d kB/s", usbh_rtlsdr.c:1084). */
+B200SDR_API int32_t b200sdr_get_counters(b200sdr_ctx *ctx, uint64_t *bytes_in, uint64_t *blocks_in,
+                                         uint64_t *busy_returns);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched path: n_captures independent captures of len_each bytes, contiguous
+ * (capture c starts at iq + c*len_each), each processed from zero state.
+ * `*_dev` functions take DEVICE pointers (inputs already resident in HBM: this is what the
+ * roofline number is measured on); `*_host` functions take HOST pointers and stream the
+ * captures through the pinned ring / copy stream, overlapping H2D with compute, and write
+ * results to host memory (this is the end-to-end number).
+ *   spectrum out : n_captures x 1024 floats
+ *   wbfm out     : n_captures x b200sdr_wbfm_audio_len(len_each) floats (48 kHz)
+ *   am out       : n_captures x b200sdr_am_audio_len(len_each) floats (8 kHz)
+ *   disc_out     : optional (may be NULL): raw discriminator, radians, at 240 kS/s,
+ *                  n_captures x b200sdr_wbfm_disc_len(len_each)
+ * All calls are asynchronous on the ctx compute stream for _dev (use b200sdr_sync) and
+ * synchronous for _host.
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t b200sdr_batch_spectrum_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures,
+                                               uint64_t len_each, float *spectrum_dev);
+B200SDR_API int32_t b200sdr_batch_wbfm_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures,
+                                           uint64_t len_each, float *audio_dev, float *disc_dev);
+B200SDR_API int32_t b200sdr_batch_am_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures,
+                                         uint64_t len_each, float *audio_dev);
+B200SDR_API int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const uint8_t *iq_host,
+                                       uint32_t n_captures, uint64_t len_each, float *spectrum_host,
+                                       float *wbfm_audio_host, float *am_audio_host);
+
+B200SDR_API uint64_t b200sdr_spectrum_frames(uint64_t len_bytes);  /* floor((L-1024)/512)+1, 0 if L<1024 */
+B200SDR_API uint64_t b200sdr_wbfm_disc_len(uint64_t len_bytes);    /* ceil(L/10)                          */
+B200SDR_API uint64_t b200sdr_wbfm_audio_len(uint64_t len_bytes);   /* ceil(ceil(L/10)/5)                  */
+B200SDR_API uint64_t b200sdr_am_audio_len(uint64_t len_bytes);     /* ceil(2*ceil(ceil(L/20)/10)/3)       */
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone IQ conversion (kernel K2): out[2n] = (I_n - 127.5) * w[n mod 1024],
+ * out[2n+1] = (Q_n - 127.5) * w[n mod 1024]; window RECT gives the exact, unscaled
+ * conversion.  Host pointers; `len` bytes in, `len` floats out.
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t b200sdr_convert_cf32(b200sdr_ctx *ctx, const uint8_t *iq_host, uint32_t len, uint32_t window,
+                                         float *out_host);
+B200SDR_API int32_t b200sdr_convert_cf32_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64_t len, uint32_t window,
+                                             float *out_dev);
+
+/* The FIR taps / window the device uses (float, as uploaded), for parity against the oracle. */
+B200SDR_API int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *out, uint32_t capacity,
+                                     uint32_t *n_taps);
+B200SDR_API int32_t b200sdr_get_window(b200sdr_ctx *ctx, uint32_t window, float *out1024);
+
+/* Read back the device copy of the most recently ingested block (ingest parity checks). */
+B200SDR_API int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capacity, uint32_t *len);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic captures generated on the device (include/b200sdr_synth.h), for benchmarks:
+ * capture c gets seed B200SDR_SYNTH_SEED_BASE + first_capture + c.
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t b200sdr_synth_fill_dev(b200sdr_ctx *ctx, uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
+                                           uint32_t kind, uint64_t first_capture);
+/* Same generator on the host (no device work), so callers can feed the streaming path. */
+B200SDR_API int32_t b200sdr_synth_fill_host(uint8_t *iq_host, uint32_t n_captures, uint64_t len_each, uint32_t kind,
+                                            uint64_t first_capture);
+
+/* Device memory helpers so a pure-C host driver needs no CUDA headers. */
+B200SDR_API int32_t b200sdr_dev_alloc(b200sdr_ctx *ctx, uint64_t bytes, void **out_dev);
+B200SDR_API int32_t b200sdr_dev_free(b200sdr_ctx *ctx, void *dev);
+B200SDR_API int32_t b200sdr_host_alloc_pinned(b200sdr_ctx *ctx, uint64_t bytes, void **out_host);
+B200SDR_API int32_t b200sdr_host_free_pinned(b200sdr_ctx *ctx, void *host);
+B200SDR_API int32_t b200sdr_copy_to_host(b200sdr_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes);
+B200SDR_API int32_t b200sdr_copy_to_dev(b200sdr_ctx *ctx, void *dst_dev, const void *src_host, uint64_t bytes);
+
+/* Timing of device work on the ctx compute stream with CUDA events (bench.py). */
+B200SDR_API int32_t b200sdr_timer_start(b200sdr_ctx *ctx);
+B200SDR_API int32_t b200sdr_timer_stop_ms(b200sdr_ctx *ctx, float *ms);
+/* Number of kernels this library has launched since ctx creation. */
+B200SDR_API uint64_t b200sdr_kernel_launches(b200sdr_ctx *ctx);
+B200SDR_API const char *b200sdr_last_error(b200sdr_ctx *ctx);
+B200SDR_API const char *b200sdr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SDR_H */

@@ -1,0 +1,466 @@
+/*
+ * golden.c -- CPU golden model ("oracle B") for the IQ sample-processing path.
+ * TEST INFRASTRUCTURE ONLY -- see golden.h for the rules and the pinning status.
+ *
+ * What it follows in the reference (paths relative to /root/reference; RTL/ =
+ * Middlewares/ST/STM32_USB_Host_Library/Class/RTLSDR/):
+ *   gold_ingest_copy    restates USB_ReadPacket, HAL_Driver/Src/stm32f7xx_ll_usb.c:792-803
+ *                       (checked bit-for-bit against the real file in oracle/_ref).
+ *   everything else     has NO counterpart in the reference (README.md:29-34: FFT / demod are
+ *                       "next tasks").  The shapes follow the CMSIS-DSP entry points the
+ *                       reference vendors as declarations only -- arm_cfft_f32 (1024-pt complex
+ *                       FFT, CMSIS/core/arm_math.h:2149, arm_const_structs.h:55),
+ *                       arm_cmplx_mag_squared_f32 (arm_math.h:4693), arm_fir_decimate_f32
+ *                       (arm_math.h:3307) -- and the frozen parameters of SURVEY.md section 8d.
+ *
+ * Definitions (L complex input samples x[n] = (I_n-127.5) + j(Q_n-127.5), zero state):
+ *   spectrum  X_m[k] = sum_{n<1024} w[n] x[512 m + n] e^{-2 pi i k n/1024}, m < F,
+ *             F = floor((L-1024)/512)+1;  mean: P[k] = (1/F) sum_m |X_m[k]|^2;
+ *             EMA: P <- (1-beta) P + beta |X_m|^2, P = 0 before frame 0.
+ *   WBFM      y1[m] = sum_{k<80} h1[k] x[10 m - k]            (m < ceil(L/10), x[<0] = 0)
+ *             d[m]  = atan2(Im, Re) of y1[m] conj(y1[m-1])     (y1[-1] = 0, so d[0] = 0)
+ *             e[m]  = e[m-1] + alpha (d[m] - e[m-1])           (e[-1] = 0, alpha = 1-exp(-1/18))
+ *             a[p]  = sum_{k<50} h2[k] e[5 p - k]              (p < ceil(M1/5))
+ *   AM        y1[m] = sum_{k<80} g1[k] x[20 m - k]; y2[q] = sum_{k<200} g2[k] y1[10 q - k]
+ *             r[q]  = |y2[q]|; b[q] = r[q] - r[q-1] + rho b[q-1]  (rho = 0.999, r[-1]=b[-1]=0)
+ *             a[s]  = sum_{k<48} g3[k] v[3 s - k], v[2q] = b[q], v[odd] = 0   (s < ceil(2 M2/3))
+ *   taps      Kaiser-windowed sinc, sum(h) = gain:
+ *             h1: 80 taps, fc 100 kHz/2.4 MHz, beta 8, gain 1/127.5
+ *             h2: 50 taps, fc 16 kHz/240 kHz, beta 5, gain 240000/(2 pi 75000)
+ *             g1: 80 taps, fc 55 kHz/2.4 MHz, beta 6, gain 1/127.5
+ *             g2: 200 taps, fc 5.2 kHz/120 kHz, beta 6, gain 1
+ *             g3: 48 taps, fc 3.6 kHz/24 kHz, beta 6, gain 2
+ */
+#define _GNU_SOURCE
+#include "golden.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../include/b200sdr_synth.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#ifdef GOLD_F32
+#define R_ATAN2 atan2f
+#define R_SQRT sqrtf
+#else
+#define R_ATAN2 atan2
+#define R_SQRT sqrt
+#endif
+
+int gold_sizeof_real(void) { return (int)sizeof(real); }
+
+/* ---- ingest: restatement of USB_ReadPacket (stm32f7xx_ll_usb.c:792-803): (len+3)/4 whole
+ * 32-bit words are written, so up to 3 bytes past `len` are overwritten. Returns bytes written. */
+size_t gold_ingest_copy(uint8_t *dest, const uint8_t *fifo_bytes, uint16_t len)
+{
+    uint32_t count32b = ((uint32_t)len + 3u) / 4u;
+    for (uint32_t i = 0; i < count32b; i++, dest += 4) {
+        uint32_t wv;
+        memcpy(&wv, fifo_bytes + 4u * i, 4);
+        memcpy(dest, &wv, 4);
+    }
+    return (size_t)count32b * 4u;
+}
+
+/* ---- conversion ------------------------------------------------------------------------- */
+void gold_convert(const uint8_t *iq, size_t n, real *out)
+{
+    for (size_t i = 0; i < 2 * n; ++i) out[i] = (real)iq[i] - (real)127.5;
+}
+
+void gold_window(int kind, int n, real *w)
+{
+    for (int i = 0; i < n; ++i) {
+        double a = 2.0 * M_PI * (double)i / (double)n;
+        double v = 1.0;
+        if (kind == GOLD_WIN_HANN) v = 0.5 - 0.5 * cos(a);
+        else if (kind == GOLD_WIN_BLACKMAN) v = 0.42 - 0.5 * cos(a) + 0.08 * cos(2.0 * a);
+        w[i] = (real)v;
+    }
+}
+
+void gold_convert_window(const uint8_t *iq, size_t n, int window, real *out)
+{
+    real w[GOLD_NFFT];
+    gold_window(window, GOLD_NFFT, w);
+    for (size_t i = 0; i < n; ++i) {
+        out[2 * i] = ((real)iq[2 * i] - (real)127.5) * w[i % GOLD_NFFT];
+        out[2 * i + 1] = ((real)iq[2 * i + 1] - (real)127.5) * w[i % GOLD_NFFT];
+    }
+}
+
+/* ---- FFT: iterative radix-2 decimation in time, twiddles from cos/sin directly ---------- */
+typedef struct {
+    int n;
+    real *wr, *wi; /* n/2 twiddles e^{-2 pi i k / n} */
+    int *rev;
+} fft_plan;
+
+static fft_plan g_plans[17];
+static pthread_mutex_t g_plan_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static const fft_plan *get_plan(int n)
+{
+    int lg = 0;
+    while ((1 << lg) < n) lg++;
+    pthread_mutex_lock(&g_plan_lock);
+    fft_plan *p = &g_plans[lg];
+    if (p->n != n) {
+        p->wr = (real *)malloc(sizeof(real) * (size_t)(n / 2 + 1));
+        p->wi = (real *)malloc(sizeof(real) * (size_t)(n / 2 + 1));
+        p->rev = (int *)malloc(sizeof(int) * (size_t)n);
+        for (int k = 0; k < n / 2; ++k) {
+            double a = -2.0 * M_PI * (double)k / (double)n;
+            p->wr[k] = (real)cos(a);
+            p->wi[k] = (real)sin(a);
+        }
+        for (int i = 0; i < n; ++i) {
+            int r = 0;
+            for (int b = 0; b < lg; ++b)
+                if (i & (1 << b)) r |= 1 << (lg - 1 - b);
+            p->rev[i] = r;
+        }
+        __sync_synchronize();
+        p->n = n;
+    }
+    pthread_mutex_unlock(&g_plan_lock);
+    return p;
+}
+
+void gold_fft(real *re, real *im, int n)
+{
+    const fft_plan *p = get_plan(n);
+    for (int i = 0; i < n; ++i) {
+        int r = p->rev[i];
+        if (r > i) {
+            real t = re[i]; re[i] = re[r]; re[r] = t;
+            t = im[i]; im[i] = im[r]; im[r] = t;
+        }
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        int half = len >> 1, step = n / len;
+        for (int base = 0; base < n; base += len) {
+            for (int k = 0; k < half; ++k) {
+                real wr = p->wr[k * step], wi = p->wi[k * step];
+                int a = base + k, b = a + half;
+                real tr = re[b] * wr - im[b] * wi;
+                real ti = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - tr; im[b] = im[a] - ti;
+                re[a] = re[a] + tr; im[a] = im[a] + ti;
+            }
+        }
+    }
+}
+
+void gold_dft_naive(const double *re, const double *im, int n, double *ore, double *oim)
+{
+    for (int k = 0; k < n; ++k) {
+        long double sr = 0, si = 0;
+        for (int t = 0; t < n; ++t) {
+            long long kt = ((long long)k * t) % n;
+            long double a = -2.0L * 3.141592653589793238462643383279502884L * (long double)kt / (long double)n;
+            long double c = cosl(a), s = sinl(a);
+            sr += (long double)re[t] * c - (long double)im[t] * s;
+            si += (long double)re[t] * s + (long double)im[t] * c;
+        }
+        ore[k] = (double)sr; oim[k] = (double)si;
+    }
+}
+
+/* ---- spectrum --------------------------------------------------------------------------- */
+uint64_t gold_spectrum(const uint8_t *iq, size_t n, int window, int avg_mode, double beta, real *out)
+{
+    real w[GOLD_NFFT], re[GOLD_NFFT], im[GOLD_NFFT];
+    real acc[GOLD_NFFT];
+    gold_window(window, GOLD_NFFT, w);
+    for (int k = 0; k < GOLD_NFFT; ++k) acc[k] = 0;
+    if (n < GOLD_NFFT) {
+        for (int k = 0; k < GOLD_NFFT; ++k) out[k] = 0;
+        return 0;
+    }
+    uint64_t frames = (uint64_t)((n - GOLD_NFFT) / GOLD_HOP) + 1u;
+    for (uint64_t m = 0; m < frames; ++m) {
+        const uint8_t *p = iq + 2u * (size_t)GOLD_HOP * m;
+        for (int i = 0; i < GOLD_NFFT; ++i) {
+            re[i] = ((real)p[2 * i] - (real)127.5) * w[i];
+            im[i] = ((real)p[2 * i + 1] - (real)127.5) * w[i];
+        }
+        gold_fft(re, im, GOLD_NFFT);
+        if (avg_mode == GOLD_AVG_EMA) {
+            for (int k = 0; k < GOLD_NFFT; ++k)
+                acc[k] = (real)(1.0 - beta) * acc[k] + (real)beta * (re[k] * re[k] + im[k] * im[k]);
+        } else {
+            for (int k = 0; k < GOLD_NFFT; ++k) acc[k] += re[k] * re[k] + im[k] * im[k];
+        }
+    }
+    if (avg_mode == GOLD_AVG_EMA) {
+        for (int k = 0; k < GOLD_NFFT; ++k) out[k] = acc[k];
+    } else {
+        for (int k = 0; k < GOLD_NFFT; ++k) out[k] = acc[k] / (real)frames;
+    }
+    return frames;
+}
+
+/* ---- filter design ---------------------------------------------------------------------- */
+static double bessel_i0(double x)
+{
+    double sum = 1.0, term = 1.0, q = x * x / 4.0;
+    for (int k = 1; k < 500; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-21 * sum) break;
+    }
+    return sum;
+}
+
+void gold_kaiser_lowpass(int ntaps, double fc, double beta, double gain, double *h)
+{
+    double mid = 0.5 * (double)(ntaps - 1), sum = 0.0, i0b = bessel_i0(beta);
+    for (int k = 0; k < ntaps; ++k) {
+        double t = (double)k - mid;
+        double x = 2.0 * fc * t;
+        double sinc = (fabs(x) < 1e-12) ? 1.0 : sin(M_PI * x) / (M_PI * x);
+        double r = t / mid;
+        double arg = 1.0 - r * r;
+        if (arg < 0.0) arg = 0.0;
+        double wk = bessel_i0(beta * sqrt(arg)) / i0b;
+        h[k] = 2.0 * fc * sinc * wk;
+        sum += h[k];
+    }
+    for (int k = 0; k < ntaps; ++k) h[k] *= gain / sum;
+}
+
+int gold_taps(int which, double *h)
+{
+    switch (which) {
+    case GOLD_TAPS_FM1: gold_kaiser_lowpass(80, 100000.0 / 2400000.0, 8.0, 1.0 / 127.5, h); return 80;
+    case GOLD_TAPS_FM2: gold_kaiser_lowpass(50, 16000.0 / 240000.0, 5.0, 240000.0 / (2.0 * M_PI * 75000.0), h); return 50;
+    case GOLD_TAPS_AM1: gold_kaiser_lowpass(80, 55000.0 / 2400000.0, 6.0, 1.0 / 127.5, h); return 80;
+    case GOLD_TAPS_AM2: gold_kaiser_lowpass(200, 5200.0 / 120000.0, 6.0, 1.0, h); return 200;
+    case GOLD_TAPS_AM3: gold_kaiser_lowpass(48, 3600.0 / 24000.0, 6.0, 2.0, h); return 48;
+    default: return 0;
+    }
+}
+
+double gold_deemph_alpha(void) { return 1.0 - exp(-1.0 / (240000.0 * 75e-6)); }
+double gold_dcblock_rho(void) { return 0.999; }
+
+static size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+size_t gold_wbfm_disc_len(size_t n) { return ceil_div(n, 10); }
+size_t gold_wbfm_audio_len(size_t n) { return ceil_div(ceil_div(n, 10), 5); }
+size_t gold_am_audio_len(size_t n) { return ceil_div(2 * ceil_div(ceil_div(n, 20), 10), 3); }
+
+/* y[m] = sum_k h[k] x[D m - k], complex x from u8, m < ceil(n/D) */
+static void fir_decim_u8(const uint8_t *iq, size_t n, const real *h, int ntaps, int D, real *y)
+{
+    size_t M = ceil_div(n, (size_t)D);
+    for (size_t m = 0; m < M; ++m) {
+        size_t c = (size_t)D * m;
+        int kmax = ntaps - 1;
+        if ((size_t)kmax > c) kmax = (int)c;
+        real sr = 0, si = 0;
+        const uint8_t *p = iq + 2 * c;
+        for (int k = 0; k <= kmax; ++k) {
+            sr += h[k] * ((real)p[-2 * k] - (real)127.5);
+            si += h[k] * ((real)p[-2 * k + 1] - (real)127.5);
+        }
+        y[2 * m] = sr; y[2 * m + 1] = si;
+    }
+}
+
+/* y[m] = sum_k h[k] x[D m - k], complex x (interleaved real) */
+static void fir_decim_c(const real *x, size_t n, const real *h, int ntaps, int D, real *y)
+{
+    size_t M = ceil_div(n, (size_t)D);
+    for (size_t m = 0; m < M; ++m) {
+        size_t c = (size_t)D * m;
+        int kmax = ntaps - 1;
+        if ((size_t)kmax > c) kmax = (int)c;
+        real sr = 0, si = 0;
+        const real *p = x + 2 * c;
+        for (int k = 0; k <= kmax; ++k) {
+            sr += h[k] * p[-2 * k];
+            si += h[k] * p[-2 * k + 1];
+        }
+        y[2 * m] = sr; y[2 * m + 1] = si;
+    }
+}
+
+/* y[m] = sum_k h[k] x[D m - k], real x */
+static void fir_decim_r(const real *x, size_t n, const real *h, int ntaps, int D, real *y)
+{
+    size_t M = ceil_div(n, (size_t)D);
+    for (size_t m = 0; m < M; ++m) {
+        size_t c = (size_t)D * m;
+        int kmax = ntaps - 1;
+        if ((size_t)kmax > c) kmax = (int)c;
+        real s = 0;
+        const real *p = x + c;
+        for (int k = 0; k <= kmax; ++k) s += h[k] * p[-k];
+        y[m] = s;
+    }
+}
+
+static void taps_as_real(int which, real *h, int *n)
+{
+    double hd[256];
+    *n = gold_taps(which, hd);
+    for (int k = 0; k < *n; ++k) h[k] = (real)hd[k];
+}
+
+void gold_wbfm_stage1(const uint8_t *iq, size_t n, real *y1)
+{
+    real h1[256]; int n1;
+    taps_as_real(GOLD_TAPS_FM1, h1, &n1);
+    fir_decim_u8(iq, n, h1, n1, 10, y1);
+}
+
+void gold_wbfm(const uint8_t *iq, size_t n, real *audio, real *disc)
+{
+    real h1[256], h2[256]; int n1, n2;
+    taps_as_real(GOLD_TAPS_FM1, h1, &n1);
+    taps_as_real(GOLD_TAPS_FM2, h2, &n2);
+    size_t M1 = gold_wbfm_disc_len(n);
+    real *y1 = (real *)malloc(sizeof(real) * 2 * (M1 + 1));
+    real *e = (real *)malloc(sizeof(real) * (M1 + 1));
+    fir_decim_u8(iq, n, h1, n1, 10, y1);
+    real alpha = (real)gold_deemph_alpha();
+    real pr = 0, pi = 0, es = 0;
+    for (size_t m = 0; m < M1; ++m) {
+        real cr = y1[2 * m], ci = y1[2 * m + 1];
+        real zr = cr * pr + ci * pi;  /* Re(y conj(p)) */
+        real zi = ci * pr - cr * pi;  /* Im(y conj(p)) */
+        real d = R_ATAN2(zi, zr);
+        if (disc) disc[m] = d;
+        es = es + alpha * (d - es);
+        e[m] = es;
+        pr = cr; pi = ci;
+    }
+    fir_decim_r(e, M1, h2, n2, 5, audio);
+    free(y1); free(e);
+}
+
+void gold_am(const uint8_t *iq, size_t n, real *audio)
+{
+    real g1[256], g2[256], g3[256]; int n1, n2, n3;
+    taps_as_real(GOLD_TAPS_AM1, g1, &n1);
+    taps_as_real(GOLD_TAPS_AM2, g2, &n2);
+    taps_as_real(GOLD_TAPS_AM3, g3, &n3);
+    size_t M1 = ceil_div(n, 20), M2 = ceil_div(M1, 10), M3 = ceil_div(2 * M2, 3);
+    real *y1 = (real *)malloc(sizeof(real) * 2 * (M1 + 1));
+    real *y2 = (real *)malloc(sizeof(real) * 2 * (M2 + 1));
+    real *b = (real *)malloc(sizeof(real) * (M2 + 1));
+    fir_decim_u8(iq, n, g1, n1, 20, y1);
+    fir_decim_c(y1, M1, g2, n2, 10, y2);
+    real rho = (real)gold_dcblock_rho(), rp = 0, bp = 0;
+    for (size_t q = 0; q < M2; ++q) {
+        real r = R_SQRT(y2[2 * q] * y2[2 * q] + y2[2 * q + 1] * y2[2 * q + 1]);
+        real v = r - rp + rho * bp;
+        b[q] = v; rp = r; bp = v;
+    }
+    for (size_t s = 0; s < M3; ++s) {
+        size_t c = 3 * s; /* index into the zero-stuffed stream v[i], v[2q] = b[q] */
+        real acc = 0;
+        for (int k = 0; k < n3; ++k) {
+            if ((size_t)k > c) break;
+            size_t i = c - (size_t)k;
+            if (i & 1u) continue;
+            size_t q = i >> 1;
+            if (q < M2) acc += g3[k] * b[q];
+        }
+        audio[s] = acc;
+    }
+    free(y1); free(y2); free(b);
+}
+
+/* ---- synthetic captures ------------------------------------------------------------------ */
+static float g_lut[B200SDR_SYNTH_LUT_SIZE + 1];
+static int g_lut_ready = 0;
+static void lut_init(void)
+{
+    if (g_lut_ready) return;
+    for (unsigned i = 0; i <= B200SDR_SYNTH_LUT_SIZE; ++i)
+        g_lut[i] = (float)sin(2.0 * M_PI * (double)(i % B200SDR_SYNTH_LUT_SIZE) / (double)B200SDR_SYNTH_LUT_SIZE);
+    __sync_synchronize();
+    g_lut_ready = 1;
+}
+const float *gold_synth_lut(void) { lut_init(); return g_lut; }
+
+void gold_synth_fill(uint8_t *iq, uint32_t n_captures, uint64_t len_each, uint32_t kind, uint64_t first_capture)
+{
+    lut_init();
+    for (uint32_t c = 0; c < n_captures; ++c) {
+        uint64_t seed = B200SDR_SYNTH_SEED_BASE + first_capture + c;
+        uint8_t *p = iq + (uint64_t)c * len_each;
+        for (uint64_t n = 0; n < len_each / 2; ++n)
+            b200sdr_synth_sample(g_lut, kind, seed, n, &p[2 * n], &p[2 * n + 1]);
+    }
+}
+
+/* ---- CPU timing ---------------------------------------------------------------------------
+ * `n_blocks` distinct blocks of n_each complex samples, contiguous in iq; `threads` POSIX
+ * threads take blocks round-robin.  The block is first copied with the reference's word-granular
+ * FIFO copy (gold_ingest_copy in <=65024-byte URBs of 512-byte packets, USBH/Src/usbh_ioreq.c:220),
+ * then processed.  Returns wall seconds (CLOCK_MONOTONIC). */
+typedef struct {
+    const uint8_t *iq; size_t n_each; uint32_t n_blocks; int tid, threads; int kind; real *out; size_t out_each;
+} work_t;
+
+static void *worker(void *arg)
+{
+    work_t *w = (work_t *)arg;
+    size_t bytes = 2 * w->n_each;
+    uint8_t *buf = (uint8_t *)malloc(bytes + 8);
+    for (uint32_t b = (uint32_t)w->tid; b < w->n_blocks; b += (uint32_t)w->threads) {
+        const uint8_t *src = w->iq + (size_t)b * bytes;
+        for (size_t off = 0; off < bytes; off += 512) {
+            size_t l = bytes - off < 512 ? bytes - off : 512;
+            gold_ingest_copy(buf + off, src + off, (uint16_t)l);
+        }
+        real *o = w->out + (size_t)b * w->out_each;
+        if (w->kind == 0) gold_spectrum(buf, w->n_each, GOLD_WIN_HANN, GOLD_AVG_MEAN, 0.0, o);
+        else if (w->kind == 1) gold_wbfm(buf, w->n_each, o, NULL);
+        else gold_am(buf, w->n_each, o);
+    }
+    free(buf);
+    return NULL;
+}
+
+static double run_timed(int kind, const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out,
+                        size_t out_each)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    work_t ws[256];
+    get_plan(GOLD_NFFT);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; ++t) {
+        ws[t] = (work_t){iq, n_each, n_blocks, t, threads, kind, out, out_each};
+        pthread_create(&th[t], NULL, worker, &ws[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+double gold_time_spectrum(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out)
+{
+    return run_timed(0, iq, n_each, n_blocks, threads, out, GOLD_NFFT);
+}
+double gold_time_wbfm(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out)
+{
+    return run_timed(1, iq, n_each, n_blocks, threads, out, gold_wbfm_audio_len(n_each));
+}
+double gold_time_am(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out)
+{
+    return run_timed(2, iq, n_each, n_blocks, threads, out, gold_am_audio_len(n_each));
+}
