@@ -66,7 +66,7 @@ extern "C" {
 #define B200SDR_AM_DECIM1     20u
 #define B200SDR_AM_TAPS1      80u
 #define B200SDR_AM_DECIM2     10u
-#define B200SDR_AM_TAPS2      200u
+#define B200SDR_AM_TAPS2      120u
 #define B200SDR_AM_UP3        2u
 #define B200SDR_AM_DECIM3     3u
 #define B200SDR_AM_TAPS3      48u

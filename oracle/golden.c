@@ -21,14 +21,14 @@
  *             d[m]  = atan2(Im, Re) of y1[m] conj(y1[m-1])     (y1[-1] = 0, so d[0] = 0)
  *             e[m]  = e[m-1] + alpha (d[m] - e[m-1])           (e[-1] = 0, alpha = 1-exp(-1/18))
  *             a[p]  = sum_{k<50} h2[k] e[5 p - k]              (p < ceil(M1/5))
- *   AM        y1[m] = sum_{k<80} g1[k] x[20 m - k]; y2[q] = sum_{k<200} g2[k] y1[10 q - k]
+ *   AM        y1[m] = sum_{k<80} g1[k] x[20 m - k]; y2[q] = sum_{k<120} g2[k] y1[10 q - k]
  *             r[q]  = |y2[q]|; b[q] = r[q] - r[q-1] + rho b[q-1]  (rho = 0.999, r[-1]=b[-1]=0)
  *             a[s]  = sum_{k<48} g3[k] v[3 s - k], v[2q] = b[q], v[odd] = 0   (s < ceil(2 M2/3))
  *   taps      Kaiser-windowed sinc, sum(h) = gain:
  *             h1: 80 taps, fc 100 kHz/2.4 MHz, beta 8, gain 1/127.5
  *             h2: 50 taps, fc 16 kHz/240 kHz, beta 5, gain 240000/(2 pi 75000)
  *             g1: 80 taps, fc 55 kHz/2.4 MHz, beta 6, gain 1/127.5
- *             g2: 200 taps, fc 5.2 kHz/120 kHz, beta 6, gain 1
+ *             g2: 120 taps, fc 5.0 kHz/120 kHz, beta 6, gain 1
  *             g3: 48 taps, fc 3.6 kHz/24 kHz, beta 6, gain 2
  */
 #define _GNU_SOURCE
@@ -243,7 +243,7 @@ int gold_taps(int which, double *h)
     case GOLD_TAPS_FM1: gold_kaiser_lowpass(80, 100000.0 / 2400000.0, 8.0, 1.0 / 127.5, h); return 80;
     case GOLD_TAPS_FM2: gold_kaiser_lowpass(50, 16000.0 / 240000.0, 5.0, 240000.0 / (2.0 * M_PI * 75000.0), h); return 50;
     case GOLD_TAPS_AM1: gold_kaiser_lowpass(80, 55000.0 / 2400000.0, 6.0, 1.0 / 127.5, h); return 80;
-    case GOLD_TAPS_AM2: gold_kaiser_lowpass(200, 5200.0 / 120000.0, 6.0, 1.0, h); return 200;
+    case GOLD_TAPS_AM2: gold_kaiser_lowpass(120, 5000.0 / 120000.0, 6.0, 1.0, h); return 120;
     case GOLD_TAPS_AM3: gold_kaiser_lowpass(48, 3600.0 / 24000.0, 6.0, 2.0, h); return 48;
     default: return 0;
     }
@@ -337,7 +337,7 @@ void gold_wbfm(const uint8_t *iq, size_t n, real *audio, real *disc)
         real cr = y1[2 * m], ci = y1[2 * m + 1];
         real zr = cr * pr + ci * pi;  /* Re(y conj(p)) */
         real zi = ci * pr - cr * pi;  /* Im(y conj(p)) */
-        real d = R_ATAN2(zi, zr);
+        real d = (m == 0) ? (real)0 : R_ATAN2(zi, zr); /* y1[-1] = 0: d[0] is DEFINED as 0 (atan2 of signed zeros is not) */
         if (disc) disc[m] = d;
         es = es + alpha * (d - es);
         e[m] = es;

@@ -1,0 +1,917 @@
+/*
+ * api.cu -- implementation of the C ABI in include/b200sdr.h: context, pinned ingest ring,
+ * copy / compute streams, streaming state, batched launches.
+ *
+ * Reference call shape being replaced (see include/b200sdr.h for the line citations): the
+ * superloop polls the class FSM; in RTLSDR_XFER_COMPLETE the 512-byte (or larger) block in
+ * `CommItf.buff` is stable until the next URB is submitted.  Here the host driver calls
+ * process_samples(block, len, ctx) at that point; the block goes pinned-ring slot -> H2D on the
+ * copy stream -> chains on the compute stream, and the caller gets its buffer back at once.
+ *
+ * No CPU fallback: every result comes from the CUDA kernels in this directory; if CUDA is not
+ * usable, b200sdr_create fails.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/b200sdr.h"
+#include "misc_kernels.cuh"
+#include "plan.h"
+
+namespace {
+
+constexpr uint32_t kCarryMax = 2048;         /* spectrum carry: < 1024 samples                    */
+constexpr uint32_t kFmLeftMax = 240;         /* < one 120-sample chunk                            */
+constexpr uint32_t kAmLeftMax = 400;         /* < one 200-sample chunk                            */
+constexpr uint64_t kWaveBytesDefault = 384ull << 20;
+
+struct AudioFifo {
+    float *d_buf = nullptr;   /* device FIFO storage (linear, compacted on pop)                    */
+    uint32_t capacity = 0;    /* floats                                                            */
+    uint32_t count = 0;       /* valid floats starting at d_buf[0]                                 */
+};
+
+} // namespace
+
+struct b200sdr_ctx {
+    b200sdr_config cfg{};
+    int device = 0, sm_count = 148;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    uint64_t launches = 0;
+    char err[256] = {0};
+
+    /* constants on the device */
+    float *d_window[3] = {nullptr, nullptr, nullptr};
+    float2 *d_twiddle = nullptr;
+    float *d_lut = nullptr;
+    std::vector<float> h_taps[5];
+    std::vector<float> h_window[3];
+
+    /* workspaces (grown on demand) */
+    float *d_partials = nullptr; size_t partials_floats = 0;
+    float *d_env = nullptr; size_t env_floats = 0;
+    uint8_t *d_wave[2] = {nullptr, nullptr}; size_t wave_bytes = 0;
+    cudaEvent_t ev_wave_copied[2] = {nullptr, nullptr}, ev_wave_done[2] = {nullptr, nullptr};
+
+    /* ingest ring */
+    uint8_t *h_ring = nullptr;          /* pinned: ring_slots x slot_bytes                          */
+    uint8_t *d_ring = nullptr;          /* device mirror of the slots                               */
+    std::vector<cudaEvent_t> ev_copied;   /* H2D of slot done (pinned slot reusable)                */
+    std::vector<cudaEvent_t> ev_consumed; /* chains have taken the device slot                      */
+    std::vector<uint8_t> slot_used;
+    uint32_t ring_head = 0;
+    bool slot_acquired = false;
+    uint64_t bytes_in = 0, blocks_in = 0, busy_returns = 0;
+    uint32_t last_len = 0, last_slot = 0;
+
+    /* streaming: spectrum */
+    uint8_t *d_spec_buf = nullptr;  /* [carry | block]                                              */
+    uint8_t *d_bounce = nullptr;
+    uint32_t spec_have = 0;         /* bytes currently in d_spec_buf                                */
+    float *d_spec_acc = nullptr;    /* running sum (mean) or EMA state, 1024 floats                 */
+    uint64_t spec_frames = 0;
+    /* streaming: WBFM */
+    uint8_t *d_fm_buf = nullptr; uint32_t fm_left = 0; uint64_t fm_chunks = 0;
+    FmState *d_fm_state = nullptr; AudioFifo fm_fifo;
+    /* streaming: AM */
+    uint8_t *d_am_buf = nullptr; uint32_t am_left = 0; uint64_t am_chunks = 0;
+    AmFrontState *d_amf_state = nullptr; AmBackState *d_amb_state = nullptr; AudioFifo am_fifo;
+    float *d_am_env_stream = nullptr;
+};
+
+namespace {
+
+int fail(b200sdr_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        if (e != cudaSuccess) snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(c->err, sizeof c->err, "%s", what);
+    }
+    return code;
+}
+
+#define CU(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) return fail(ctx, B200SDR_FAIL, #call, e_);             \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_floats(b200sdr_ctx *ctx, float **p, size_t *have, size_t want)
+{
+    if (*have >= want) return B200SDR_OK;
+    if (*p) { CU(cudaStreamSynchronize(ctx->s_compute)); CU(cudaFree(*p)); *p = nullptr; *have = 0; }
+    CU(cudaMalloc((void **)p, want * sizeof(float)));
+    *have = want;
+    return B200SDR_OK;
+}
+
+/* ---- launches --------------------------------------------------------------------------- */
+int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t stride, uint64_t len_bytes,
+                    bool ema, const float *carry, float carry_scale, float scale_override, bool use_scale_override,
+                    float *out_dev)
+{
+    b200::SpectrumPlan pl = b200::plan_spectrum(len_bytes, n_captures, (uint32_t)ctx->sm_count);
+    if (pl.frames == 0) return B200SDR_OK;
+    int rc = ensure_floats(ctx, &ctx->d_partials, &ctx->partials_floats, (size_t)n_captures * pl.ctas_per_capture * 1024);
+    if (rc) return rc;
+    SpectrumParams p{};
+    p.iq = iq_dev;
+    p.capture_stride = stride;
+    p.frames = pl.frames;
+    p.frames_per_warp = pl.frames_per_warp;
+    p.window = ctx->d_window[ctx->cfg.window];
+    p.twiddle = ctx->d_twiddle;
+    p.partials = ctx->d_partials;
+    p.ctas_per_capture = pl.ctas_per_capture;
+    p.ema_beta = ctx->cfg.ema_beta;
+    p.ema_log2_decay = log2f(1.0f - ctx->cfg.ema_beta);
+    dim3 grid(pl.ctas_per_capture, n_captures);
+    if (ema) k_spectrum<true><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
+    else k_spectrum<false><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    float scale = ema ? 1.0f : 1.0f / (float)pl.frames;
+    if (use_scale_override) scale = scale_override;
+    k_spectrum_finalize<<<dim3(4, n_captures), 256, 0, ctx->s_compute>>>(ctx->d_partials, pl.ctas_per_capture, scale,
+                                                                         carry, carry_scale, out_dev);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    return B200SDR_OK;
+}
+
+int launch_wbfm_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_bytes, float *audio,
+                      float *disc)
+{
+    b200::FmPlan pl = b200::plan_wbfm_batch(len_bytes, n_captures, (uint32_t)ctx->sm_count);
+    if (pl.n_tiles == 0) return B200SDR_OK;
+    FmParams p{};
+    p.iq = iq_dev;
+    p.capture_stride = len_bytes;
+    p.capture_bytes = len_bytes;
+    p.m1 = pl.m1;
+    p.n_tiles = pl.n_tiles;
+    p.total_chunks = pl.total_chunks;
+    p.tiles_per_segment = pl.tiles_per_segment;
+    p.audio = audio;
+    p.audio_stride = b200::wbfm_audio_len(len_bytes);
+    p.disc = disc;
+    p.disc_stride = pl.m1;
+    k_wbfm<<<dim3(pl.segments, n_captures), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int launch_am_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_bytes, float *audio)
+{
+    b200::AmPlan pl = b200::plan_am_batch(len_bytes, n_captures, (uint32_t)ctx->sm_count);
+    if (pl.n_tiles == 0) return B200SDR_OK;
+    int rc = ensure_floats(ctx, &ctx->d_env, &ctx->env_floats, (size_t)n_captures * pl.q_count);
+    if (rc) return rc;
+    AmFrontParams p{};
+    p.iq = iq_dev;
+    p.capture_stride = len_bytes;
+    p.capture_bytes = len_bytes;
+    p.q_count = pl.q_count;
+    p.n_tiles = pl.n_tiles;
+    p.total_chunks = pl.total_chunks;
+    p.tiles_per_segment = pl.tiles_per_segment;
+    p.env = ctx->d_env;
+    p.env_stride = pl.q_count;
+    k_am_front<<<dim3(pl.segments, n_captures), B200_AM_THREADS, B200_AM_SMEM_BYTES, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    AmBackParams b{};
+    b.env = ctx->d_env;
+    b.env_stride = pl.q_count;
+    b.q_count = pl.q_count;
+    b.audio = audio;
+    b.audio_stride = pl.audio_len;
+    k_am_back<<<n_captures, B200_AMB_THREADS, 0, ctx->s_compute>>>(b);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    return B200SDR_OK;
+}
+
+bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+/* ---- streaming steps (all on the compute stream, after the block is in d_ring[slot]) ---- */
+int stream_spectrum(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
+{
+    CU(cudaMemcpyAsync(ctx->d_spec_buf + ctx->spec_have, d_block, len, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    ctx->spec_have += len;
+    const uint64_t frames = b200::spectrum_frames(ctx->spec_have);
+    if (frames == 0) return B200SDR_OK;
+    const bool ema = ctx->cfg.avg_mode == B200SDR_AVG_EMA;
+    /* mean: acc += sum |X|^2 ; EMA: acc = (1-beta)^F acc + sum beta (1-beta)^(F-1-m) |X_m|^2 */
+    const float carry_scale = ema ? powf(1.0f - ctx->cfg.ema_beta, (float)frames) : 1.0f;
+    int rc = launch_spectrum(ctx, ctx->d_spec_buf, 1, 0, ctx->spec_have, ema, ctx->d_spec_acc, carry_scale, 1.0f, true,
+                             ctx->d_spec_acc);
+    if (rc) return rc;
+    ctx->spec_frames += frames;
+    const uint32_t consumed = (uint32_t)(frames * 1024u); /* 512 samples x 2 bytes per frame */
+    const uint32_t keep = ctx->spec_have - consumed;
+    CU(cudaMemcpyAsync(ctx->d_bounce, ctx->d_spec_buf + consumed, keep, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    CU(cudaMemcpyAsync(ctx->d_spec_buf, ctx->d_bounce, keep, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    ctx->spec_have = keep;
+    return B200SDR_OK;
+}
+
+int stream_wbfm(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
+{
+    CU(cudaMemcpyAsync(ctx->d_fm_buf + ctx->fm_left, d_block, len, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    const uint32_t have = ctx->fm_left + len;
+    const uint32_t n_chunks = have / (2 * B200_FM_CHUNK);
+    if (n_chunks == 0) { ctx->fm_left = have; return B200SDR_OK; }
+    FmParams p{};
+    p.iq = ctx->d_fm_buf;
+    p.capture_bytes = (uint64_t)n_chunks * 2 * B200_FM_CHUNK;
+    p.m1 = (uint64_t)n_chunks * B200_FM_OPT;
+    p.m_base = ctx->fm_chunks * B200_FM_OPT;
+    p.total_chunks = n_chunks;
+    p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_FM_THREADS);
+    p.tiles_per_segment = p.n_tiles;
+    const uint64_t a0 = b200::ceil_div(p.m_base, B200_FM_D2), a1 = b200::ceil_div(p.m_base + p.m1, B200_FM_D2);
+    const uint32_t n_audio = (uint32_t)(a1 - a0);
+    if (ctx->fm_fifo.count + n_audio > ctx->fm_fifo.capacity) return fail(ctx, B200SDR_FAIL, "WBFM audio FIFO overflow");
+    p.audio = ctx->fm_fifo.d_buf + ctx->fm_fifo.count;
+    p.audio_base = a0;
+    p.state = ctx->d_fm_state;
+    k_wbfm<<<dim3(1, 1), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->fm_fifo.count += n_audio;
+    ctx->fm_chunks += n_chunks;
+    const uint32_t consumed = n_chunks * 2 * B200_FM_CHUNK;
+    ctx->fm_left = have - consumed;
+    if (ctx->fm_left)
+        CU(cudaMemcpyAsync(ctx->d_fm_buf, ctx->d_fm_buf + consumed, ctx->fm_left, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    return B200SDR_OK;
+}
+
+int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
+{
+    CU(cudaMemcpyAsync(ctx->d_am_buf + ctx->am_left, d_block, len, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    const uint32_t have = ctx->am_left + len;
+    const uint32_t n_chunks = have / (2 * B200_AM_CHUNK);
+    if (n_chunks == 0) { ctx->am_left = have; return B200SDR_OK; }
+    const uint64_t a0 = (2 * ctx->am_chunks + 2) / 3, a1 = (2 * (ctx->am_chunks + n_chunks) + 2) / 3;
+    const uint32_t n_audio = (uint32_t)(a1 - a0);
+    if (ctx->am_fifo.count + n_audio > ctx->am_fifo.capacity) return fail(ctx, B200SDR_FAIL, "AM audio FIFO overflow");
+    AmFrontParams p{};
+    p.iq = ctx->d_am_buf;
+    p.capture_bytes = (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
+    p.q_count = n_chunks;
+    p.total_chunks = n_chunks;
+    p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_AM_THREADS);
+    p.tiles_per_segment = p.n_tiles;
+    p.env = ctx->d_am_env_stream;
+    p.state = ctx->d_amf_state;
+    k_am_front<<<dim3(1, 1), B200_AM_THREADS, B200_AM_SMEM_BYTES, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    AmBackParams b{};
+    b.env = ctx->d_am_env_stream;
+    b.q_count = n_chunks;
+    b.q_base = ctx->am_chunks;
+    b.audio = ctx->am_fifo.d_buf + ctx->am_fifo.count;
+    b.audio_base = a0;
+    b.state = ctx->d_amb_state;
+    k_am_back<<<1, B200_AMB_THREADS, 0, ctx->s_compute>>>(b);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    ctx->am_fifo.count += n_audio;
+    ctx->am_chunks += n_chunks;
+    const uint32_t consumed = n_chunks * 2 * B200_AM_CHUNK;
+    ctx->am_left = have - consumed;
+    if (ctx->am_left)
+        CU(cudaMemcpyAsync(ctx->d_am_buf, ctx->d_am_buf + consumed, ctx->am_left, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    return B200SDR_OK;
+}
+
+int reset_stream_state(b200sdr_ctx *ctx)
+{
+    ctx->spec_have = 0; ctx->spec_frames = 0;
+    ctx->fm_left = 0; ctx->fm_chunks = 0; ctx->fm_fifo.count = 0;
+    ctx->am_left = 0; ctx->am_chunks = 0; ctx->am_fifo.count = 0;
+    CU(cudaMemsetAsync(ctx->d_spec_acc, 0, 1024 * sizeof(float), ctx->s_compute));
+    CU(cudaMemsetAsync(ctx->d_fm_state, 0, sizeof(FmState), ctx->s_compute));
+    CU(cudaMemsetAsync(ctx->d_amf_state, 0, sizeof(AmFrontState), ctx->s_compute));
+    CU(cudaMemsetAsync(ctx->d_amb_state, 0, sizeof(AmBackState), ctx->s_compute));
+    return B200SDR_OK;
+}
+
+const float *synth_lut_host()
+{
+    static float lut[B200SDR_SYNTH_LUT_SIZE + 1];
+    static bool ready = false;
+    if (!ready) {
+        for (unsigned i = 0; i <= B200SDR_SYNTH_LUT_SIZE; ++i)
+            lut[i] = (float)sin(2.0 * b200::kPi * (double)(i % B200SDR_SYNTH_LUT_SIZE) / (double)B200SDR_SYNTH_LUT_SIZE);
+        ready = true;
+    }
+    return lut;
+}
+
+int commit_slot(b200sdr_ctx *ctx, uint32_t slot, uint32_t len)
+{
+    uint8_t *h_slot = ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes;
+    uint8_t *d_slot = ctx->d_ring + (size_t)slot * ctx->cfg.slot_bytes;
+    /* the device slot may still be read by the chains of `ring_slots` blocks ago */
+    if (ctx->slot_used[slot]) CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_consumed[slot], 0));
+    CU(cudaMemcpyAsync(d_slot, h_slot, len, cudaMemcpyHostToDevice, ctx->s_copy));
+    CU(cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy));
+    CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[slot], 0));
+    int rc = B200SDR_OK;
+    if (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM) { rc = stream_spectrum(ctx, d_slot, len); if (rc) return rc; }
+    if (ctx->cfg.chains & B200SDR_CHAIN_WBFM) { rc = stream_wbfm(ctx, d_slot, len); if (rc) return rc; }
+    if (ctx->cfg.chains & B200SDR_CHAIN_AM) { rc = stream_am(ctx, d_slot, len); if (rc) return rc; }
+    CU(cudaEventRecord(ctx->ev_consumed[slot], ctx->s_compute));
+    ctx->slot_used[slot] = 1;
+    ctx->last_len = len;
+    ctx->last_slot = slot;
+    ctx->bytes_in += len;
+    ctx->blocks_in += 1;
+    ctx->ring_head = (slot + 1) % ctx->cfg.ring_slots;
+    return B200SDR_OK;
+}
+
+/* would this block overflow an audio FIFO?  checked before anything is enqueued */
+bool fifo_room(b200sdr_ctx *ctx, uint32_t len)
+{
+    if ((ctx->cfg.chains & B200SDR_CHAIN_WBFM) && ctx->fm_fifo.count + len / 100 + 8 > ctx->fm_fifo.capacity) return false;
+    if ((ctx->cfg.chains & B200SDR_CHAIN_AM) && ctx->am_fifo.count + len / 600 + 8 > ctx->am_fifo.capacity) return false;
+    return true;
+}
+
+/* is the pinned slot free (its previous H2D finished)? */
+int slot_ready(b200sdr_ctx *ctx, uint32_t slot)
+{
+    if (!ctx->slot_used[slot]) return B200SDR_OK;
+    cudaError_t q = cudaEventQuery(ctx->ev_copied[slot]);
+    if (q == cudaSuccess) return B200SDR_OK;
+    if (q == cudaErrorNotReady) { ctx->busy_returns++; return B200SDR_BUSY; }
+    return fail(ctx, B200SDR_FAIL, "cudaEventQuery", q);
+}
+
+int pop_fifo(b200sdr_ctx *ctx, AudioFifo &f, float *out, uint32_t capacity, uint32_t *n_out)
+{
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    uint32_t n = f.count < capacity ? f.count : capacity;
+    if (n) CU(cudaMemcpy(out, f.d_buf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    const uint32_t rest = f.count - n;
+    if (rest && n) {
+        /* compact through the bounce buffer in pieces (rare: caller's buffer was too small) */
+        std::vector<float> tmp(rest);
+        CU(cudaMemcpy(tmp.data(), f.d_buf + n, (size_t)rest * sizeof(float), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(f.d_buf, tmp.data(), (size_t)rest * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    f.count = rest;
+    if (n_out) *n_out = n;
+    return B200SDR_OK;
+}
+
+} // namespace
+
+/* ============================================================================================ */
+extern "C" {
+
+const char *b200sdr_version(void) { return "b200sdr 0.1 (sm_100a)"; }
+
+void b200sdr_default_config(b200sdr_config *cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = (uint32_t)sizeof *cfg;
+    cfg->device = 0;
+    cfg->chains = B200SDR_CHAIN_SPECTRUM | B200SDR_CHAIN_WBFM | B200SDR_CHAIN_AM;
+    cfg->window = B200SDR_WINDOW_HANN;
+    cfg->avg_mode = B200SDR_AVG_MEAN;
+    cfg->ema_beta = 0.1f;
+    cfg->ring_slots = 8;
+    cfg->slot_bytes = 262144; /* DEFAULT_BUF_LENGTH, RTL/Inc/usbh_rtlsdr.h:277-278 */
+    cfg->audio_capacity = 1u << 20;
+}
+
+int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
+{
+    if (!cfg_in || !out_ctx) return B200SDR_FAIL;
+    *out_ctx = nullptr;
+    b200sdr_config cfg = *cfg_in;
+    if (cfg.struct_size != sizeof(b200sdr_config)) return B200SDR_NOT_SUPPORTED;
+    if (cfg.window > B200SDR_WINDOW_BLACKMAN || cfg.avg_mode > B200SDR_AVG_EMA) return B200SDR_NOT_SUPPORTED;
+    if (cfg.ring_slots < 2 || cfg.ring_slots > 1024) return B200SDR_NOT_SUPPORTED;
+    if (cfg.slot_bytes < 4 || (cfg.slot_bytes & 3u)) return B200SDR_NOT_SUPPORTED; /* multiple-of-4 rule */
+    if (cfg.avg_mode == B200SDR_AVG_EMA && !(cfg.ema_beta > 0.0f && cfg.ema_beta < 1.0f)) return B200SDR_NOT_SUPPORTED;
+    if (cfg.audio_capacity < 4096) cfg.audio_capacity = 4096;
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || cfg.device < 0 || cfg.device >= n_dev)
+        return B200SDR_FAIL; /* no CUDA device: there is no CPU path */
+    b200sdr_ctx *ctx = new (std::nothrow) b200sdr_ctx();
+    if (!ctx) return B200SDR_FAIL;
+    ctx->cfg = cfg;
+    ctx->device = cfg.device;
+    DeviceGuard guard(ctx->device);
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "b200sdr_create: %s: %s\n", #call, cudaGetErrorString(e_));        \
+            b200sdr_destroy(ctx);                                                              \
+            return B200SDR_FAIL;                                                               \
+        }                                                                                      \
+    } while (0)
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major < 10) {
+        fprintf(stderr, "b200sdr_create: device is sm_%d%d; this library is built for sm_100a only\n", prop.major, prop.minor);
+        b200sdr_destroy(ctx);
+        return B200SDR_FAIL;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev_t0));
+    CK(cudaEventCreate(&ctx->ev_t1));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_wave_copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_wave_done[i], cudaEventDisableTiming));
+    }
+    CK(cudaFuncSetAttribute(k_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_SPEC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_SPEC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_wbfm, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_FM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_am_front, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_AM_SMEM_BYTES));
+
+    /* constants */
+    for (unsigned w = 0; w < 3; ++w) {
+        ctx->h_window[w] = b200::make_window(w, 1024);
+        CK(cudaMalloc((void **)&ctx->d_window[w], 1024 * sizeof(float)));
+        CK(cudaMemcpy(ctx->d_window[w], ctx->h_window[w].data(), 1024 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<float2> tw(1024);
+        b200::fill_twiddles(tw.data());
+        CK(cudaMalloc((void **)&ctx->d_twiddle, 1024 * sizeof(float2)));
+        CK(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void **)&ctx->d_lut, (B200SDR_SYNTH_LUT_SIZE + 1) * sizeof(float)));
+        CK(cudaMemcpy(ctx->d_lut, synth_lut_host(), (B200SDR_SYNTH_LUT_SIZE + 1) * sizeof(float), cudaMemcpyHostToDevice));
+        FmTaps ft{};
+        b200::fill_fm_taps(ft);
+        CK(cudaMemcpyToSymbol(c_fm_taps, &ft, sizeof ft));
+        AmTaps at{};
+        b200::fill_am_taps(at);
+        CK(cudaMemcpyToSymbol(c_am_taps, &at, sizeof at));
+        for (unsigned t = 0; t < 5; ++t) {
+            std::vector<double> h = b200::design_taps(t);
+            ctx->h_taps[t].assign(h.begin(), h.end());
+        }
+    }
+    /* ingest ring + streaming buffers */
+    const size_t ring_bytes = (size_t)cfg.ring_slots * cfg.slot_bytes;
+    CK(cudaHostAlloc((void **)&ctx->h_ring, ring_bytes, cudaHostAllocDefault));
+    CK(cudaMalloc((void **)&ctx->d_ring, ring_bytes));
+    ctx->ev_copied.resize(cfg.ring_slots);
+    ctx->ev_consumed.resize(cfg.ring_slots);
+    ctx->slot_used.assign(cfg.ring_slots, 0);
+    for (uint32_t i = 0; i < cfg.ring_slots; ++i) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+    }
+    CK(cudaMalloc((void **)&ctx->d_spec_buf, (size_t)cfg.slot_bytes + kCarryMax + 64));
+    CK(cudaMalloc((void **)&ctx->d_bounce, kCarryMax + 64));
+    CK(cudaMalloc((void **)&ctx->d_spec_acc, 1024 * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->d_fm_buf, (size_t)cfg.slot_bytes + kFmLeftMax + 64));
+    CK(cudaMalloc((void **)&ctx->d_am_buf, (size_t)cfg.slot_bytes + kAmLeftMax + 64));
+    CK(cudaMalloc((void **)&ctx->d_fm_state, sizeof(FmState)));
+    CK(cudaMalloc((void **)&ctx->d_amf_state, sizeof(AmFrontState)));
+    CK(cudaMalloc((void **)&ctx->d_amb_state, sizeof(AmBackState)));
+    CK(cudaMalloc((void **)&ctx->d_am_env_stream, ((size_t)cfg.slot_bytes / 400 + 8) * sizeof(float)));
+    ctx->fm_fifo.capacity = cfg.audio_capacity;
+    ctx->am_fifo.capacity = cfg.audio_capacity;
+    CK(cudaMalloc((void **)&ctx->fm_fifo.d_buf, (size_t)cfg.audio_capacity * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->am_fifo.d_buf, (size_t)cfg.audio_capacity * sizeof(float)));
+    if (reset_stream_state(ctx) != B200SDR_OK) { b200sdr_destroy(ctx); return B200SDR_FAIL; }
+    CK(cudaStreamSynchronize(ctx->s_compute));
+#undef CK
+    *out_ctx = ctx;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_destroy(b200sdr_ctx *ctx)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto e : ctx->ev_copied) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_consumed) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_wave_copied[i]) cudaEventDestroy(ctx->ev_wave_copied[i]);
+        if (ctx->ev_wave_done[i]) cudaEventDestroy(ctx->ev_wave_done[i]);
+        if (ctx->d_wave[i]) cudaFree(ctx->d_wave[i]);
+    }
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    void *dev_ptrs[] = {ctx->d_ring, ctx->d_spec_buf, ctx->d_bounce, ctx->d_spec_acc, ctx->d_fm_buf, ctx->d_am_buf,
+                        ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
+                        ctx->am_fifo.d_buf, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
+                        ctx->d_lut, ctx->d_partials, ctx->d_env};
+    for (void *p : dev_ptrs) if (p) cudaFree(p);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    delete ctx;
+    return B200SDR_OK;
+}
+
+/* ---- streaming ---------------------------------------------------------------------------- */
+int32_t process_samples(const uint8_t *iq, uint32_t len, void *vctx)
+{
+    b200sdr_ctx *ctx = (b200sdr_ctx *)vctx;
+    if (!ctx || !iq) return B200SDR_FAIL;
+    if (len == 0) return B200SDR_OK;
+    if ((len & 3u) || len > ctx->cfg.slot_bytes) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4 and <= slot_bytes");
+    if (ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "a ring slot is acquired; commit it first");
+    DeviceGuard guard(ctx->device);
+    if (!fifo_room(ctx, len)) { ctx->busy_returns++; return fail(ctx, B200SDR_BUSY, "audio FIFO full: call b200sdr_get_audio"); }
+    const uint32_t slot = ctx->ring_head;
+    int rc = slot_ready(ctx, slot);
+    if (rc) return rc;
+    memcpy(ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes, iq, len);
+    return commit_slot(ctx, slot, len);
+}
+
+int32_t b200sdr_ring_acquire(b200sdr_ctx *ctx, uint8_t **slot_ptr, uint32_t *slot_bytes)
+{
+    if (!ctx || !slot_ptr) return B200SDR_FAIL;
+    if (ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "slot already acquired");
+    DeviceGuard guard(ctx->device);
+    const uint32_t slot = ctx->ring_head;
+    int rc = slot_ready(ctx, slot);
+    if (rc) return rc;
+    *slot_ptr = ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes;
+    if (slot_bytes) *slot_bytes = ctx->cfg.slot_bytes;
+    ctx->slot_acquired = true;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_ring_commit(b200sdr_ctx *ctx, uint32_t len)
+{
+    if (!ctx) return B200SDR_FAIL;
+    if (!ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "no slot acquired");
+    if ((len & 3u) || len > ctx->cfg.slot_bytes) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4 and <= slot_bytes");
+    if (!fifo_room(ctx, len)) { ctx->busy_returns++; return fail(ctx, B200SDR_BUSY, "audio FIFO full: call b200sdr_get_audio"); }
+    ctx->slot_acquired = false;
+    if (len == 0) return B200SDR_OK;
+    DeviceGuard guard(ctx->device);
+    return commit_slot(ctx, ctx->ring_head, len);
+}
+
+int32_t b200sdr_sync(b200sdr_ctx *ctx)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_copy));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_reset(b200sdr_ctx *ctx)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    int rc = b200sdr_sync(ctx);
+    if (rc) return rc;
+    return reset_stream_state(ctx);
+}
+
+int32_t b200sdr_get_spectrum(b200sdr_ctx *ctx, float *out1024, uint64_t *n_frames)
+{
+    if (!ctx || !out1024) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaMemcpy(out1024, ctx->d_spec_acc, 1024 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (ctx->cfg.avg_mode == B200SDR_AVG_MEAN && ctx->spec_frames) {
+        const float s = 1.0f / (float)ctx->spec_frames;
+        for (int k = 0; k < 1024; ++k) out1024[k] *= s;
+    }
+    if (n_frames) *n_frames = ctx->spec_frames;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_get_audio(b200sdr_ctx *ctx, uint32_t chain, float *out, uint32_t capacity, uint32_t *n_out)
+{
+    if (!ctx || !out) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    if (chain == B200SDR_CHAIN_WBFM) return pop_fifo(ctx, ctx->fm_fifo, out, capacity, n_out);
+    if (chain == B200SDR_CHAIN_AM) return pop_fifo(ctx, ctx->am_fifo, out, capacity, n_out);
+    return fail(ctx, B200SDR_NOT_SUPPORTED, "chain has no audio output");
+}
+
+int32_t b200sdr_get_counters(b200sdr_ctx *ctx, uint64_t *bytes_in, uint64_t *blocks_in, uint64_t *busy_returns)
+{
+    if (!ctx) return B200SDR_FAIL;
+    if (bytes_in) *bytes_in = ctx->bytes_in;
+    if (blocks_in) *blocks_in = ctx->blocks_in;
+    if (busy_returns) *busy_returns = ctx->busy_returns;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capacity, uint32_t *len)
+{
+    if (!ctx || !out) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_copy));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    uint32_t n = ctx->last_len < capacity ? ctx->last_len : capacity;
+    if (n) CU(cudaMemcpy(out, ctx->d_ring + (size_t)ctx->last_slot * ctx->cfg.slot_bytes, n, cudaMemcpyDeviceToHost));
+    if (len) *len = ctx->last_len;
+    return B200SDR_OK;
+}
+
+/* ---- batched, device-resident -------------------------------------------------------------- */
+uint64_t b200sdr_spectrum_frames(uint64_t len_bytes) { return b200::spectrum_frames(len_bytes); }
+uint64_t b200sdr_wbfm_disc_len(uint64_t len_bytes) { return b200::wbfm_disc_len(len_bytes); }
+uint64_t b200sdr_wbfm_audio_len(uint64_t len_bytes) { return b200::wbfm_audio_len(len_bytes); }
+uint64_t b200sdr_am_audio_len(uint64_t len_bytes) { return b200::am_audio_len(len_bytes); }
+
+int32_t b200sdr_batch_spectrum_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
+                                   float *spectrum_dev)
+{
+    if (!ctx || !iq_dev || !spectrum_dev) return B200SDR_FAIL;
+    if (n_captures == 0) return B200SDR_OK;
+    if ((len_each & 3u) || n_captures > 65535u || ((uintptr_t)iq_dev & 1u))
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "len_each must be a multiple of 4, n_captures <= 65535");
+    DeviceGuard guard(ctx->device);
+    if (b200::spectrum_frames(len_each) == 0) {
+        CU(cudaMemsetAsync(spectrum_dev, 0, (size_t)n_captures * 1024 * sizeof(float), ctx->s_compute));
+        return B200SDR_OK;
+    }
+    return launch_spectrum(ctx, iq_dev, n_captures, len_each, len_each, ctx->cfg.avg_mode == B200SDR_AVG_EMA, nullptr,
+                           0.0f, 0.0f, false, spectrum_dev);
+}
+
+int32_t b200sdr_batch_wbfm_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
+                               float *audio_dev, float *disc_dev)
+{
+    if (!ctx || !iq_dev || !audio_dev) return B200SDR_FAIL;
+    if (n_captures == 0 || len_each == 0) return B200SDR_OK;
+    if ((len_each & 15u) || !aligned16(iq_dev) || n_captures > 65535u)
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "batched WBFM needs 16-byte aligned captures (len_each % 16 == 0)");
+    DeviceGuard guard(ctx->device);
+    return launch_wbfm_batch(ctx, iq_dev, n_captures, len_each, audio_dev, disc_dev);
+}
+
+int32_t b200sdr_batch_am_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
+                             float *audio_dev)
+{
+    if (!ctx || !iq_dev || !audio_dev) return B200SDR_FAIL;
+    if (n_captures == 0 || len_each == 0) return B200SDR_OK;
+    if ((len_each & 15u) || !aligned16(iq_dev) || n_captures > 65535u)
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "batched AM needs 16-byte aligned captures (len_each % 16 == 0)");
+    DeviceGuard guard(ctx->device);
+    return launch_am_batch(ctx, iq_dev, n_captures, len_each, audio_dev);
+}
+
+/* ---- batched, host buffers: captures stream through two device wave buffers so the H2D copy of
+ * wave w+1 overlaps the kernels of wave w; results go straight back to host memory ------------ */
+int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const uint8_t *iq_host, uint32_t n_captures,
+                           uint64_t len_each, float *spectrum_host, float *wbfm_audio_host, float *am_audio_host)
+{
+    if (!ctx || !iq_host) return B200SDR_FAIL;
+    if (n_captures == 0 || len_each == 0) return B200SDR_OK;
+    if (len_each & 15u) return fail(ctx, B200SDR_NOT_SUPPORTED, "len_each must be a multiple of 16");
+    if ((chains & B200SDR_CHAIN_SPECTRUM) && !spectrum_host) return B200SDR_FAIL;
+    if ((chains & B200SDR_CHAIN_WBFM) && !wbfm_audio_host) return B200SDR_FAIL;
+    if ((chains & B200SDR_CHAIN_AM) && !am_audio_host) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    uint64_t per_wave = kWaveBytesDefault / len_each;
+    if (per_wave < 1) per_wave = 1;
+    if (per_wave > n_captures) per_wave = n_captures;
+    const size_t wave_bytes = (size_t)per_wave * len_each;
+    if (ctx->wave_bytes < wave_bytes) {
+        CU(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->d_wave[i]) CU(cudaFree(ctx->d_wave[i]));
+            ctx->d_wave[i] = nullptr;
+            CU(cudaMalloc((void **)&ctx->d_wave[i], wave_bytes));
+        }
+        ctx->wave_bytes = wave_bytes;
+    }
+    const uint64_t fm_len = b200::wbfm_audio_len(len_each), am_len = b200::am_audio_len(len_each);
+    float *d_spec = nullptr, *d_fm = nullptr, *d_am = nullptr;
+    /* per-wave result buffers, double buffered with the wave */
+    if (chains & B200SDR_CHAIN_SPECTRUM) CU(cudaMalloc((void **)&d_spec, 2 * per_wave * 1024 * sizeof(float)));
+    if (chains & B200SDR_CHAIN_WBFM) CU(cudaMalloc((void **)&d_fm, 2 * per_wave * fm_len * sizeof(float)));
+    if (chains & B200SDR_CHAIN_AM) CU(cudaMalloc((void **)&d_am, 2 * per_wave * am_len * sizeof(float)));
+    int rc = B200SDR_OK;
+    bool used[2] = {false, false};
+    uint32_t wave = 0;
+    for (uint64_t c0 = 0; c0 < n_captures && rc == B200SDR_OK; c0 += per_wave, ++wave) {
+        const int b = (int)(wave & 1);
+        const uint32_t nc = (uint32_t)((n_captures - c0 < per_wave) ? n_captures - c0 : per_wave);
+        if (used[b]) CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_wave_done[b], 0));
+        CU(cudaMemcpyAsync(ctx->d_wave[b], iq_host + c0 * len_each, (size_t)nc * len_each, cudaMemcpyHostToDevice, ctx->s_copy));
+        CU(cudaEventRecord(ctx->ev_wave_copied[b], ctx->s_copy));
+        CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_wave_copied[b], 0));
+        if (chains & B200SDR_CHAIN_SPECTRUM) {
+            float *o = d_spec + (size_t)b * per_wave * 1024;
+            rc = b200sdr_batch_spectrum_dev(ctx, ctx->d_wave[b], nc, len_each, o);
+            if (rc) break;
+            CU(cudaMemcpyAsync(spectrum_host + c0 * 1024, o, (size_t)nc * 1024 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
+        }
+        if (chains & B200SDR_CHAIN_WBFM) {
+            float *o = d_fm + (size_t)b * per_wave * fm_len;
+            rc = launch_wbfm_batch(ctx, ctx->d_wave[b], nc, len_each, o, nullptr);
+            if (rc) break;
+            CU(cudaMemcpyAsync(wbfm_audio_host + c0 * fm_len, o, (size_t)nc * fm_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
+        }
+        if (chains & B200SDR_CHAIN_AM) {
+            float *o = d_am + (size_t)b * per_wave * am_len;
+            rc = launch_am_batch(ctx, ctx->d_wave[b], nc, len_each, o);
+            if (rc) break;
+            CU(cudaMemcpyAsync(am_audio_host + c0 * am_len, o, (size_t)nc * am_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
+        }
+        CU(cudaEventRecord(ctx->ev_wave_done[b], ctx->s_compute));
+        used[b] = true;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_copy), e2 = cudaStreamSynchronize(ctx->s_compute);
+    if (d_spec) cudaFree(d_spec);
+    if (d_fm) cudaFree(d_fm);
+    if (d_am) cudaFree(d_am);
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "copy stream", e1);
+    if (e2 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "compute stream", e2);
+    return B200SDR_OK;
+}
+
+/* ---- K2 ------------------------------------------------------------------------------------ */
+int32_t b200sdr_convert_cf32_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64_t len, uint32_t window, float *out_dev)
+{
+    if (!ctx || !iq_dev || !out_dev) return B200SDR_FAIL;
+    if (window > B200SDR_WINDOW_BLACKMAN) return fail(ctx, B200SDR_NOT_SUPPORTED, "bad window");
+    if ((len & 15u) || !aligned16(iq_dev) || !aligned16(out_dev))
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "device conversion needs len % 16 == 0 and 16-byte aligned pointers");
+    if (len == 0) return B200SDR_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t n16 = len / 16;
+    const float *w = window == B200SDR_WINDOW_RECT ? nullptr : ctx->d_window[window];
+    k_convert_cf32<<<(unsigned)((n16 + 255) / 256), 256, 0, ctx->s_compute>>>((const uint4 *)iq_dev, (float4 *)out_dev, n16, w);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_convert_cf32(b200sdr_ctx *ctx, const uint8_t *iq_host, uint32_t len, uint32_t window, float *out_host)
+{
+    if (!ctx || !iq_host || !out_host) return B200SDR_FAIL;
+    if (len & 3u) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4");
+    if (len == 0) return B200SDR_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t padded = ((uint64_t)len + 15u) & ~15ull;
+    uint8_t *d_in = nullptr;
+    float *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_in, padded));
+    cudaError_t e = cudaMalloc((void **)&d_out, padded * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(ctx, B200SDR_FAIL, "cudaMalloc", e); }
+    int rc = B200SDR_OK;
+    do {
+        if ((e = cudaMemsetAsync(d_in, 0, padded, ctx->s_compute)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_in, iq_host, len, cudaMemcpyHostToDevice, ctx->s_compute)) != cudaSuccess) break;
+        rc = b200sdr_convert_cf32_dev(ctx, d_in, padded, window, d_out);
+        if (rc) break;
+        if ((e = cudaMemcpyAsync(out_host, d_out, (size_t)len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(ctx->s_compute);
+    } while (0);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "convert", e);
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *out, uint32_t capacity, uint32_t *n_taps)
+{
+    if (!ctx || which > 4) return B200SDR_NOT_SUPPORTED;
+    const std::vector<float> &h = ctx->h_taps[which];
+    if (n_taps) *n_taps = (uint32_t)h.size();
+    if (out) {
+        if (capacity < h.size()) return fail(ctx, B200SDR_NOT_SUPPORTED, "capacity too small");
+        memcpy(out, h.data(), h.size() * sizeof(float));
+    }
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_get_window(b200sdr_ctx *ctx, uint32_t window, float *out1024)
+{
+    if (!ctx || !out1024 || window > 2) return B200SDR_NOT_SUPPORTED;
+    DeviceGuard guard(ctx->device);
+    CU(cudaMemcpy(out1024, ctx->d_window[window], 1024 * sizeof(float), cudaMemcpyDeviceToHost)); /* as the kernels see it */
+    return B200SDR_OK;
+}
+
+/* ---- synthetic captures -------------------------------------------------------------------- */
+int32_t b200sdr_synth_fill_dev(b200sdr_ctx *ctx, uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each, uint32_t kind,
+                               uint64_t first_capture)
+{
+    if (!ctx || !iq_dev) return B200SDR_FAIL;
+    if (kind > B200SDR_SYNTH_AM) return fail(ctx, B200SDR_NOT_SUPPORTED, "bad synth kind");
+    if ((len_each & 15u) || !aligned16(iq_dev) || n_captures > 65535u)
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "len_each must be a multiple of 16");
+    if (n_captures == 0 || len_each == 0) return B200SDR_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t groups = len_each / 16;
+    k_synth<<<dim3((unsigned)((groups + 255) / 256), n_captures), 256, 0, ctx->s_compute>>>((uint4 *)iq_dev, groups, groups, kind,
+                                                                                             first_capture, ctx->d_lut);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_synth_fill_host(uint8_t *iq_host, uint32_t n_captures, uint64_t len_each, uint32_t kind, uint64_t first_capture)
+{
+    if (!iq_host || kind > B200SDR_SYNTH_AM || (len_each & 1u)) return B200SDR_NOT_SUPPORTED;
+    const float *lut = synth_lut_host();
+    for (uint32_t c = 0; c < n_captures; ++c) {
+        uint8_t *p = iq_host + (uint64_t)c * len_each;
+        const uint64_t seed = B200SDR_SYNTH_SEED_BASE + first_capture + c;
+        for (uint64_t n = 0; n < len_each / 2; ++n) b200sdr_synth_sample(lut, kind, seed, n, &p[2 * n], &p[2 * n + 1]);
+    }
+    return B200SDR_OK;
+}
+
+/* ---- memory / timing helpers --------------------------------------------------------------- */
+int32_t b200sdr_dev_alloc(b200sdr_ctx *ctx, uint64_t bytes, void **out_dev)
+{
+    if (!ctx || !out_dev) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaMalloc(out_dev, bytes ? bytes : 16));
+    return B200SDR_OK;
+}
+int32_t b200sdr_dev_free(b200sdr_ctx *ctx, void *dev)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaFree(dev));
+    return B200SDR_OK;
+}
+int32_t b200sdr_host_alloc_pinned(b200sdr_ctx *ctx, uint64_t bytes, void **out_host)
+{
+    if (!ctx || !out_host) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaHostAlloc(out_host, bytes ? bytes : 16, cudaHostAllocDefault));
+    return B200SDR_OK;
+}
+int32_t b200sdr_host_free_pinned(b200sdr_ctx *ctx, void *host)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaFreeHost(host));
+    return B200SDR_OK;
+}
+int32_t b200sdr_copy_to_host(b200sdr_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return B200SDR_OK;
+}
+int32_t b200sdr_copy_to_dev(b200sdr_ctx *ctx, void *dst_dev, const void *src_host, uint64_t bytes)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return B200SDR_OK;
+}
+int32_t b200sdr_timer_start(b200sdr_ctx *ctx)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaEventRecord(ctx->ev_t0, ctx->s_compute));
+    return B200SDR_OK;
+}
+int32_t b200sdr_timer_stop_ms(b200sdr_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    CU(cudaEventRecord(ctx->ev_t1, ctx->s_compute));
+    CU(cudaEventSynchronize(ctx->ev_t1));
+    CU(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return B200SDR_OK;
+}
+uint64_t b200sdr_kernel_launches(b200sdr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+const char *b200sdr_last_error(b200sdr_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+} /* extern "C" */

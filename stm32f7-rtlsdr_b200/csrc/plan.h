@@ -1,0 +1,134 @@
+/*
+ * plan.h -- host-side launch planning shared by the C-ABI implementation (api.cu) and by the
+ * CPU emulation harness of the test-suite: output lengths, tile / segment split, constant blocks.
+ */
+#ifndef B200_PLAN_H
+#define B200_PLAN_H
+
+#include <cstdint>
+
+#include "filter_design.h"
+#include "spectrum.cuh"
+#include "wbfm.cuh"
+#include "am.cuh"
+
+namespace b200 {
+
+inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+/* lengths in complex samples L = bytes / 2 */
+inline uint64_t spectrum_frames(uint64_t len_bytes)
+{
+    const uint64_t n = len_bytes / 2;
+    return n < 1024 ? 0 : (n - 1024) / 512 + 1;
+}
+inline uint64_t wbfm_disc_len(uint64_t len_bytes) { return ceil_div(len_bytes / 2, 10); }
+inline uint64_t wbfm_audio_len(uint64_t len_bytes) { return ceil_div(wbfm_disc_len(len_bytes), 5); }
+inline uint64_t am_y2_len(uint64_t len_bytes) { return ceil_div(ceil_div(len_bytes / 2, 20), 10); }
+inline uint64_t am_audio_len(uint64_t len_bytes) { return ceil_div(2 * am_y2_len(len_bytes), 3); }
+
+/* ---- spectrum: frames per warp so that the grid has a few waves of CTAs ---- */
+struct SpectrumPlan {
+    uint32_t frames, frames_per_warp, ctas_per_capture;
+};
+inline SpectrumPlan plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count)
+{
+    SpectrumPlan pl{};
+    pl.frames = (uint32_t)spectrum_frames(len_bytes);
+    if (pl.frames == 0) return pl;
+    /* aim at >= 16 CTAs per SM over the whole batch, at most 256 frames per warp, at least 1 */
+    const uint64_t total_frames = (uint64_t)pl.frames * n_captures;
+    const uint64_t want_warps = (uint64_t)sm_count * 16 * B200_SPEC_WARPS;
+    uint64_t fpw = total_frames / want_warps;
+    if (fpw < 1) fpw = 1;
+    if (fpw > 256) fpw = 256;
+    pl.frames_per_warp = (uint32_t)fpw;
+    pl.ctas_per_capture = (uint32_t)ceil_div(pl.frames, fpw * B200_SPEC_WARPS);
+    return pl;
+}
+
+/* ---- WBFM ---- */
+struct FmPlan {
+    uint32_t n_tiles, total_chunks, tiles_per_segment, segments;
+    uint64_t m1;
+};
+/* whole captures (batched path): every stage-1 output m < ceil(L/10) */
+inline FmPlan plan_wbfm_batch(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count)
+{
+    FmPlan pl{};
+    const uint64_t n = len_bytes / 2;
+    pl.m1 = ceil_div(n, 10);
+    pl.total_chunks = (uint32_t)ceil_div(n, B200_FM_CHUNK);
+    pl.n_tiles = (uint32_t)ceil_div(pl.total_chunks, B200_FM_THREADS);
+    /* enough segments for ~6 CTAs per SM over the batch, but segments of >= 8 tiles so the
+     * one-tile pre-roll of segments > 0 stays a small overhead */
+    uint64_t want = ceil_div((uint64_t)sm_count * 6, n_captures ? n_captures : 1);
+    uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
+    if (tps < 8) tps = 8;
+    if (tps > pl.n_tiles) tps = pl.n_tiles ? pl.n_tiles : 1;
+    pl.tiles_per_segment = (uint32_t)tps;
+    pl.segments = (uint32_t)ceil_div(pl.n_tiles, tps);
+    if (pl.segments == 0) pl.segments = 1;
+    return pl;
+}
+
+inline void fill_fm_taps(FmTaps &t)
+{
+    const std::vector<double> h1 = design_taps(0), h2 = design_taps(1);
+    for (int k = 0; k < B200_FM_T1; ++k) t.h1[k] = (float)h1[k];
+    for (int k = 0; k < B200_FM_T2; ++k) t.h2[k] = (float)h2[k];
+    const double alpha = deemph_alpha(), a = 1.0 - alpha;
+    t.alpha = (float)alpha;
+    for (int i = 0; i < 16; ++i) t.apow[i] = (float)std::pow(a, i + 1);
+    const double a12 = std::pow(a, B200_FM_OPT);
+    t.a12 = (float)a12;
+    for (int s = 0; s < 5; ++s) t.a12pow[s] = (float)std::pow(a12, double(1 << s));
+    t.a384 = (float)std::pow(a12, 32.0);
+}
+
+/* ---- AM ---- */
+struct AmPlan {
+    uint32_t n_tiles, total_chunks, tiles_per_segment, segments;
+    uint64_t q_count, audio_len;
+};
+inline AmPlan plan_am_batch(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count)
+{
+    AmPlan pl{};
+    const uint64_t n = len_bytes / 2;
+    pl.q_count = am_y2_len(len_bytes);
+    pl.audio_len = am_audio_len(len_bytes);
+    pl.total_chunks = (uint32_t)ceil_div(n, B200_AM_CHUNK);
+    pl.n_tiles = (uint32_t)ceil_div(pl.total_chunks, B200_AM_THREADS);
+    uint64_t want = ceil_div((uint64_t)sm_count * 6, n_captures ? n_captures : 1);
+    uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
+    if (tps < 8) tps = 8;
+    if (tps > pl.n_tiles) tps = pl.n_tiles ? pl.n_tiles : 1;
+    pl.tiles_per_segment = (uint32_t)tps;
+    pl.segments = (uint32_t)ceil_div(pl.n_tiles, tps);
+    if (pl.segments == 0) pl.segments = 1;
+    return pl;
+}
+inline void fill_am_taps(AmTaps &t)
+{
+    const std::vector<double> g1 = design_taps(2), g2 = design_taps(3), g3 = design_taps(4);
+    for (int k = 0; k < B200_AM_T1; ++k) t.g1[k] = (float)g1[k];
+    for (int k = 0; k < B200_AM_T2; ++k) t.g2[k] = (float)g2[k];
+    for (int k = 0; k < B200_AM_T3; ++k) t.g3[k] = (float)g3[k];
+    const double rho = dcblock_rho(), rho4 = std::pow(rho, B200_AMB_PER);
+    t.rho = (float)rho;
+    t.rho4 = (float)rho4;
+    for (int s = 0; s < 6; ++s) t.rho4_pow[s] = (float)std::pow(rho4, double(1 << s));
+    for (int i = 0; i < 4; ++i) t.rho_i[i] = (float)std::pow(rho, i + 1);
+}
+
+inline void fill_twiddles(float2 *tw1024)
+{
+    for (int m = 0; m < 1024; ++m) {
+        const double a = -2.0 * kPi * m / 1024.0;
+        tw1024[m].x = (float)std::cos(a);
+        tw1024[m].y = (float)std::sin(a);
+    }
+}
+
+} // namespace b200
+#endif

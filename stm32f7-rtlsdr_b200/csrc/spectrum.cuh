@@ -1,0 +1,168 @@
+/*
+ * spectrum.cuh -- kernel K3: u8 I/Q -> window -> 1024-point FFT -> |X|^2 -> averaged spectrum,
+ * fused, one pass over the input bytes.
+ *
+ * Reference anchor: this is the consumer of `CommItf.buff` the firmware never wrote
+ * (README.md:31-32 "next task"; the commented poll at src/main.c:76-79); the intended MCU shape
+ * is arm_cfft_f32(1024) + arm_cmplx_mag_squared_f32 (CMSIS/core/arm_math.h:2149, :4693).
+ * Definition followed: oracle/golden.c gold_spectrum().
+ *
+ * Decomposition: 1024 = 32 x 32 "four-step" FFT, ONE WARP PER FRAME, 32 points per lane:
+ *   n = t + 32 j   (t = lane, j = 0..31)       k = k1 + 32 k2
+ *   pass 1 (lane t):  Y[k1] = sum_j w[n] x[n] W32^{j k1}      in registers (fft32.cuh)
+ *   twiddle:          Y[k1] *= W1024^{t k1}                    table in shared memory
+ *   transpose:        lane t -> lane k1 through a warp-private 32x33 shared tile
+ *   pass 2 (lane k1): X[k1+32 k2] = sum_t Y_t[k1] W32^{t k2}   in registers
+ *   power:            acc[k2] += |X|^2                          32 bins per lane, in registers
+ * A warp walks `frames_per_warp` consecutive frames (hop 512) and keeps the 32 x 32 bin sums in
+ * registers; the warps of a CTA are then added in a fixed order and one 1024-float partial per
+ * CTA goes to a workspace that k_spectrum_finalize sums in a fixed order -> deterministic
+ * results (no float atomics), identical for any GPU count.
+ *
+ * Input access: lane t reads the 2-byte sample n = t + 32 j straight from global memory
+ * (a warp reads 64 contiguous bytes per j; both halves of every 128-byte line are used by
+ * consecutive j, the second from L1).  Every input byte is fetched from HBM once per frame
+ * pair at most (the 50 % overlap re-read hits L2).
+ *
+ * Roofline: 2 bytes per new complex sample vs ~2100 fp32 lane-operations per frame (512 new
+ * samples) -> this chain is bound by the FP32 pipe, not by HBM; the packed
+ * FFMA2 formulation keeps the issue slots for loads / PRMT / LDS / STS free.
+ */
+#ifndef B200_SPECTRUM_CUH
+#define B200_SPECTRUM_CUH
+
+#include "fft32.cuh"
+
+#define B200_SPEC_WARPS 4
+#define B200_SPEC_THREADS (32 * B200_SPEC_WARPS)
+#define B200_SPEC_XP 33 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free */
+#define B200_SPEC_WP 36 /* window row pitch in floats */
+
+/* shared memory carve-up (bytes) */
+#define B200_SPEC_SMEM_WIN 0
+#define B200_SPEC_SMEM_TW (32 * B200_SPEC_WP * 4)
+#define B200_SPEC_SMEM_XP (B200_SPEC_SMEM_TW + 32 * 32 * 8)
+#define B200_SPEC_SMEM_BYTES (B200_SPEC_SMEM_XP + B200_SPEC_WARPS * 32 * B200_SPEC_XP * 8)
+
+#ifdef B200_EMULATED
+#define B200_DYN_SMEM(name) unsigned char *name = EMU_DYN_SMEM
+#else
+#define B200_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+struct SpectrumParams {
+    const uint8_t *iq;        /* capture c starts at iq + c * capture_stride                     */
+    uint64_t capture_stride;  /* bytes                                                           */
+    uint32_t frames;          /* frames per capture (all captures equal length)                  */
+    uint32_t frames_per_warp; /* consecutive frames walked by one warp                           */
+    const float *window;      /* 1024 floats                                                     */
+    const float2 *twiddle;    /* 1024 entries: e^{-2 pi i m / 1024}                              */
+    float *partials;          /* [capture][ctas_per_capture][1024]                               */
+    uint32_t ctas_per_capture;
+    float ema_log2_decay;     /* log2(1 - beta), EMA only                                        */
+    float ema_beta;
+};
+
+template <bool EMA>
+__global__ void __launch_bounds__(B200_SPEC_THREADS, 3) k_spectrum(SpectrumParams p)
+{
+    B200_DYN_SMEM(smem);
+    float *s_win = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_WIN);
+    c2 *s_tw = reinterpret_cast<c2 *>(smem + B200_SPEC_SMEM_TW);
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    c2 *s_xp = reinterpret_cast<c2 *>(smem + B200_SPEC_SMEM_XP) + warp * (32 * B200_SPEC_XP);
+
+    /* stage window as win[t][j] = w[t + 32 j] and twiddles as tw[k1][t] = W1024^{t k1} */
+    for (int i = tid; i < 1024; i += B200_SPEC_THREADS) {
+        int t = i & 31, j = i >> 5;
+        s_win[t * B200_SPEC_WP + j] = __ldg(p.window + i);
+        float2 w = __ldg(p.twiddle + ((t * j) & 1023));
+        s_tw[j * 32 + t] = c2_make(w.x, w.y);
+    }
+    __syncthreads();
+
+    const uint32_t capture = blockIdx.y;
+    const uint32_t warp_global = blockIdx.x * B200_SPEC_WARPS + (uint32_t)warp;
+    const uint32_t m_begin = warp_global * p.frames_per_warp;
+    uint32_t m_end = m_begin + p.frames_per_warp;
+    if (m_end > p.frames) m_end = p.frames;
+
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+
+    const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
+    const float *my_win = s_win + lane * B200_SPEC_WP;
+
+    for (uint32_t m = m_begin; m < m_end; ++m) {
+        const unsigned short *src = reinterpret_cast<const unsigned short *>(cap) + ((uint64_t)m * 512u + (uint32_t)lane);
+        c2 v[32];
+        /* load + convert + window, written to the bit-reversed slot pass 1 wants */
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * j4);
+            const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * j4 + jj;
+                uint32_t raw = (uint32_t)__ldg(src + 32 * j);
+                v[b200_bitrev5(j)] = c2_scale(c2_from_u8_lo(raw), wj[jj]);
+            }
+        }
+        b200_fft32(v); /* v[k1] = Y[k1] */
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            float wr, wi;
+            c2_get(s_tw[k1 * 32 + lane], wr, wi);
+            v[k1] = c2_cmul(v[k1], wr, wi);
+        }
+        /* transpose through the warp-private tile: row = k1 (the reader's lane), column = source lane t */
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) s_xp[k1 * B200_SPEC_XP + lane] = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[b200_bitrev5(t)] = s_xp[lane * B200_SPEC_XP + t];
+        __syncwarp();
+        b200_fft32(v); /* v[k2] = X[lane + 32 k2] */
+        if (EMA) {
+            float wgt = p.ema_beta * exp2f((float)(p.frames - 1u - m) * p.ema_log2_decay);
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) acc[k2] = fmaf(c2_norm_acc(v[k2], 0.0f), wgt, acc[k2]);
+        } else {
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) acc[k2] = c2_norm_acc(v[k2], acc[k2]);
+        }
+    }
+
+    /* fixed-order reduction over the CTA's warps, then one partial per CTA */
+    __syncthreads();
+    float *s_red = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_XP); /* [warp][1024], pitch 32*XP*2 floats */
+    float *mine = s_red + warp * (32 * B200_SPEC_XP * 2);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) mine[k2 * 32 + lane] = acc[k2]; /* bin k = lane + 32 k2 */
+    __syncthreads();
+    float *out = p.partials + ((uint64_t)capture * p.ctas_per_capture + blockIdx.x) * 1024u;
+    for (int k = tid; k < 1024; k += B200_SPEC_THREADS) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < B200_SPEC_WARPS; ++w) s += s_red[w * (32 * B200_SPEC_XP * 2) + k];
+        out[k] = s;
+    }
+}
+
+/* out[c][k] = scale * sum_i partials[c][i][k] + carry_scale * carry[k]  (fixed order) */
+__global__ void __launch_bounds__(256) k_spectrum_finalize(const float *partials, uint32_t ctas_per_capture,
+                                                           float scale, const float *carry, float carry_scale,
+                                                           float *out)
+{
+    const uint32_t capture = blockIdx.y;
+    const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    const float *src = partials + (uint64_t)capture * ctas_per_capture * 1024u + k;
+    float s = 0.0f;
+    for (uint32_t i = 0; i < ctas_per_capture; ++i) s += src[(uint64_t)i * 1024u];
+    float r = s * scale;
+    if (carry) r = fmaf(carry[(uint64_t)capture * 1024u + k], carry_scale, r);
+    out[(uint64_t)capture * 1024u + k] = r;
+}
+
+#endif

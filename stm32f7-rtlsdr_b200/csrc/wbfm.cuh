@@ -1,0 +1,352 @@
+/*
+ * wbfm.cuh -- kernel K4 (FM): u8 I/Q -> /10 polyphase FIR (80 taps) -> quadrature discriminator
+ * -> 75 us de-emphasis -> /5 FIR (50 taps) -> 48 kHz audio, fused: the IQ stream crosses HBM once
+ * and nothing but audio is written back.
+ *
+ * Reference anchor: none of this exists in the firmware (README.md:29-34); the planned MCU shape
+ * is arm_fir_decimate_f32 (CMSIS/core/arm_math.h:3307).  The RTL2832's own 32-tap hardware FIR
+ * (RTL/Inc/usbh_rtlsdr.h:340-345) runs before the bytes reach us.  Definition followed:
+ * oracle/golden.c gold_wbfm().
+ *
+ * Work split.  grid = (segments, captures).  A CTA of 128 threads walks the tiles of its segment
+ * in order; a tile is 128 x 120 input samples (30 720 bytes) brought in by one TMA bulk copy,
+ * double buffered.
+ *
+ * Stage 1 is written "input-partitioned": thread t owns input samples [a, a+120), a = tile + 120 t,
+ * converts each byte pair exactly once (PRMT + one packed FADD) and scatters it into the (at most
+ * 8) outputs y1[m] = sum_k h[k] x[10 m - k] whose window covers it.  Eight packed accumulators
+ * rotate; output i of the chunk (centre a + 10 i) completes at sample 10 i:
+ *     i = 0..7   partially complete ("heads", started in the previous thread's chunk)
+ *     i = 8..11  complete inside the chunk
+ *     i = 12..19 started here, finished by the next thread  ("tails", 8 partial sums)
+ * Thread t+1 adds thread t's tails to its heads through shared memory; the last thread's tails
+ * are carried to the next tile.  So the FIR needs NO input history at all -- a capture (or a
+ * stream) starts with zero tails, which is exactly x[n<0] = 0 -- and costs exactly 8 packed FMAs
+ * per input sample with taps held in registers (40 distinct: the filter is symmetric).
+ *
+ * The 240 kS/s stages run per tile on the 1536 fresh outputs: discriminator (atan2 of
+ * y[m] conj(y[m-1])), the de-emphasis recurrence as a fixed-shape scan (thread-serial over 12,
+ * warp shuffle scan, cross-warp carry, exact carried state between tiles), then the /5 FIR out
+ * of a shared-memory window with 49 samples of history.
+ *
+ * Segments after the first start one tile early with stores suppressed: that warms the carried
+ * state up (de-emphasis pole 0.946^1536 ~ 0).  Segment 0 and the streaming path (`state` != 0)
+ * carry exact state.
+ */
+#ifndef B200_WBFM_CUH
+#define B200_WBFM_CUH
+
+#include "cplx2.cuh"
+#include "tma.cuh"
+
+#define B200_FM_THREADS 128
+#define B200_FM_CHUNK 120                                  /* input samples per thread per tile      */
+#define B200_FM_OPT 12                                     /* stage-1 outputs per thread per tile    */
+#define B200_FM_TILE_IN (B200_FM_THREADS * B200_FM_CHUNK)  /* 15360                                  */
+#define B200_FM_TILE_OUT (B200_FM_THREADS * B200_FM_OPT)   /* 1536                                   */
+#define B200_FM_TILE_BYTES (2 * B200_FM_TILE_IN)           /* 30720                                  */
+#define B200_FM_STAGES 2
+#define B200_FM_T1 80
+#define B200_FM_T2 50
+#define B200_FM_D2 5
+#define B200_FM_HIST (B200_FM_T2 - 1) /* 49 */
+
+/* shared memory carve-up */
+#define B200_FM_SM_RAW 0
+#define B200_FM_SM_TAIL (B200_FM_SM_RAW + B200_FM_STAGES * B200_FM_TILE_BYTES)         /* c2 [129][8]  */
+#define B200_FM_SM_YLAST (B200_FM_SM_TAIL + (B200_FM_THREADS + 1) * 8 * 8)             /* c2 [129]     */
+#define B200_FM_SM_E (B200_FM_SM_YLAST + (B200_FM_THREADS + 1) * 8)                    /* float [49+1536] */
+#define B200_FM_SM_WSUM (B200_FM_SM_E + (B200_FM_HIST + B200_FM_TILE_OUT + 3) / 4 * 16) /* float [8]    */
+#define B200_FM_SM_TAILC (B200_FM_SM_WSUM + 32)                                         /* c2 [2][8]    */
+#define B200_FM_SM_YLASTC (B200_FM_SM_TAILC + 2 * 8 * 8)                                /* c2 [2]       */
+#define B200_FM_SM_BAR (B200_FM_SM_YLASTC + 16)                                         /* u64 [2]      */
+#define B200_FM_SMEM_BYTES (B200_FM_SM_BAR + 16)
+
+#ifndef B200_DYN_SMEM
+#ifdef B200_EMULATED
+#define B200_DYN_SMEM(name) unsigned char *name = EMU_DYN_SMEM
+#else
+#define B200_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+#endif
+
+/* state carried between tiles; in global memory it carries a stream from call to call */
+struct FmState {
+    float tail[16];  /* 8 packed partial sums                                  */
+    float ylast[2];  /* y1[m0-1]                                               */
+    float e_last;    /* e[m0-1]                                                */
+    float pad;
+    float e_hist[52]; /* e[m0-49 .. m0-1] in [0..48]                           */
+};
+
+struct FmTaps {
+    float h1[B200_FM_T1]; /* stage 1, includes 1/127.5                         */
+    float h2[B200_FM_T2]; /* stage 2, includes the audio gain                  */
+    float apow[16];       /* a^(i+1), i = 0..11, a = 1 - alpha                 */
+    float alpha;
+    float a12;            /* a^12                                              */
+    float a12pow[5];      /* (a^12)^(2^s), s = 0..4                            */
+    float a384;           /* (a^12)^32                                         */
+};
+
+struct FmParams {
+    const uint8_t *iq;       /* capture c at iq + c * capture_stride (16-byte aligned)                 */
+    uint64_t capture_stride; /* bytes                                                                  */
+    uint64_t capture_bytes;  /* valid bytes per capture (multiple of 16 for the batched path)          */
+    uint64_t m1;             /* stage-1 outputs per capture to produce: m < m1                         */
+    uint64_t m_base;         /* global index of the first stage-1 output of this launch (streaming)    */
+    uint32_t n_tiles;        /* tiles per capture                                                      */
+    uint32_t total_chunks;   /* 120-sample chunks per capture (the last tile may be partly filled)     */
+    uint32_t tiles_per_segment;
+    float *audio;            /* [capture][audio_stride]                                                */
+    uint64_t audio_stride;
+    uint64_t audio_base;     /* audio index of local p = 0 (streaming FIFO offset)                     */
+    float *disc;             /* optional [capture][disc_stride]                                        */
+    uint64_t disc_stride;
+    FmState *state;          /* optional [capture]: read at start, written at the end (1 segment only) */
+    uint32_t *n_audio_out;   /* optional [capture]: number of audio samples written (streaming)        */
+};
+
+/* one input sample scattered into its (up to) 8 outputs; J is the sample index in the chunk */
+template <int J>
+B200_DEV void b200_fm_scatter(c2 x, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
+{
+#pragma unroll
+    for (int i = (J + 9) / 10; i <= (J + 79) / 10; ++i) {
+        const int k = 10 * i - J;
+        acc[i & 7] = c2_fma_s(x, h[k < 40 ? k : 79 - k], acc[i & 7]);
+    }
+    if (J % 10 == 0 && J / 10 < B200_FM_OPT) {
+        head[J / 10] = acc[(J / 10) & 7];
+        acc[(J / 10) & 7] = c2_zero();
+    }
+}
+
+template <int Q>
+struct b200_fm_words {
+    B200_DEVM static void run(const uint4 *raw, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
+    {
+        const uint4 r = raw[Q];
+        b200_fm_scatter<8 * Q + 0>(c2_from_u8_lo(r.x), h, acc, head);
+        b200_fm_scatter<8 * Q + 1>(c2_from_u8_hi(r.x), h, acc, head);
+        b200_fm_scatter<8 * Q + 2>(c2_from_u8_lo(r.y), h, acc, head);
+        b200_fm_scatter<8 * Q + 3>(c2_from_u8_hi(r.y), h, acc, head);
+        b200_fm_scatter<8 * Q + 4>(c2_from_u8_lo(r.z), h, acc, head);
+        b200_fm_scatter<8 * Q + 5>(c2_from_u8_hi(r.z), h, acc, head);
+        b200_fm_scatter<8 * Q + 6>(c2_from_u8_lo(r.w), h, acc, head);
+        b200_fm_scatter<8 * Q + 7>(c2_from_u8_hi(r.w), h, acc, head);
+        b200_fm_words<Q + 1>::run(raw, h, acc, head);
+    }
+};
+template <>
+struct b200_fm_words<B200_FM_CHUNK / 8> {
+    B200_DEVM static void run(const uint4 *, const float (&)[40], c2 (&)[8], c2 (&)[B200_FM_OPT]) {}
+};
+
+#ifdef B200_EMULATED
+static FmTaps c_fm_taps;
+#else
+__constant__ FmTaps c_fm_taps;
+#endif
+
+__global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
+{
+    const FmTaps *taps = &c_fm_taps;
+    B200_DYN_SMEM(smem);
+    c2 *s_tail = reinterpret_cast<c2 *>(smem + B200_FM_SM_TAIL);
+    c2 *s_ylast = reinterpret_cast<c2 *>(smem + B200_FM_SM_YLAST);
+    float *s_e = reinterpret_cast<float *>(smem + B200_FM_SM_E);
+    float *s_wsum = reinterpret_cast<float *>(smem + B200_FM_SM_WSUM);
+    c2 *s_tailc = reinterpret_cast<c2 *>(smem + B200_FM_SM_TAILC);
+    c2 *s_ylastc = reinterpret_cast<c2 *>(smem + B200_FM_SM_YLASTC);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + B200_FM_SM_BAR);
+
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t capture = blockIdx.y;
+    const uint32_t seg = blockIdx.x;
+
+    /* tiles of this segment; segments > 0 pre-roll one tile with stores suppressed */
+    uint32_t t_begin = seg * p.tiles_per_segment;
+    uint32_t t_end = t_begin + p.tiles_per_segment;
+    if (t_end > p.n_tiles) t_end = p.n_tiles;
+    const uint32_t t_first_store = t_begin;
+    if (seg > 0) t_begin -= 1;
+    const uint32_t my_tiles = t_end > t_begin ? t_end - t_begin : 0;
+
+    const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
+
+    /* taps and scan constants -> registers */
+    float h[40];
+#pragma unroll
+    for (int k = 0; k < 40; ++k) h[k] = taps->h1[k];
+    const float alpha = taps->alpha;
+    const float a1 = 1.0f - alpha;
+    float lane_pow = 1.0f; /* (a^12)^lane */
+    for (int i = 0; i < lane; ++i) lane_pow *= taps->a12;
+
+    /* carried state */
+    if (tid < 8) {
+        float tr = 0.0f, ti = 0.0f;
+        if (p.state) { tr = p.state[capture].tail[2 * tid]; ti = p.state[capture].tail[2 * tid + 1]; }
+        s_tailc[8 + tid] = c2_make(tr, ti); /* tile 0 reads carry buffer 1 */
+    }
+    if (tid == 8) {
+        float yr = 0.0f, yi = 0.0f;
+        if (p.state) { yr = p.state[capture].ylast[0]; yi = p.state[capture].ylast[1]; }
+        s_ylastc[1] = c2_make(yr, yi);
+    }
+    if (tid == 9) s_wsum[4] = p.state ? p.state[capture].e_last : 0.0f; /* tile carry e[m0-1] */
+    if (tid >= 32 && tid < 32 + B200_FM_HIST) s_e[tid - 32] = p.state ? p.state[capture].e_hist[tid - 32] : 0.0f;
+
+    auto issue_tile = [&](uint32_t it) { /* thread 0 only */
+        const uint32_t tile = t_begin + it;
+        const uint64_t off = (uint64_t)tile * B200_FM_TILE_BYTES;
+        uint64_t bytes = p.capture_bytes > off ? p.capture_bytes - off : 0;
+        if (bytes > B200_FM_TILE_BYTES) bytes = B200_FM_TILE_BYTES;
+        bytes &= ~(uint64_t)15;
+        uint64_t *bar = s_bar + (it & 1);
+        b200_mbar_expect_tx(bar, (uint32_t)bytes);
+        if (bytes) b200_tma_load_1d(smem + B200_FM_SM_RAW + (it & 1) * B200_FM_TILE_BYTES, cap + off, (uint32_t)bytes, bar);
+    };
+    if (tid == 0) {
+        b200_mbar_init(s_bar + 0, 1);
+        b200_mbar_init(s_bar + 1, 1);
+        b200_mbar_fence_init();
+        if (my_tiles > 0) issue_tile(0);
+        if (my_tiles > 1) issue_tile(1);
+    }
+    __syncthreads();
+
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+        const uint32_t tile = t_begin + it;
+        const bool store = tile >= t_first_store;
+        const uint64_t m0 = (uint64_t)tile * B200_FM_TILE_OUT; /* first stage-1 output of the tile (local index) */
+        /* last thread of the tile holding a whole chunk: it owns the carries to the next tile */
+        int last = (int)(p.total_chunks - tile * B200_FM_THREADS) - 1;
+        if (last > B200_FM_THREADS - 1) last = B200_FM_THREADS - 1;
+        const int par = (int)(it & 1);
+
+        /* ---- stage 1: scatter FIR over this thread's 120 samples ---- */
+        b200_mbar_wait(s_bar + (it & 1), (it >> 1) & 1);
+        c2 acc[8], head[B200_FM_OPT];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = c2_zero();
+        const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_FM_SM_RAW + (it & 1) * B200_FM_TILE_BYTES +
+                                                           tid * (2 * B200_FM_CHUNK));
+        b200_fm_words<0>::run(raw, h, acc, head);
+        /* tails: outputs 12..19 live in acc[i & 7] -> next thread's slots 0..7 */
+        {
+            c2 *tail_dst = (tid == last) ? s_tailc + par * 8 : s_tail + (tid + 1) * 8;
+#pragma unroll
+            for (int i = 12; i < 20; ++i) tail_dst[i - 12] = acc[i & 7];
+        }
+        __syncthreads(); /* S1: raw buffer consumed, tails visible */
+        if (tid == 0 && it + 2 < my_tiles) issue_tile(it + 2);
+        {
+            const c2 *tail_src = (tid == 0) ? s_tailc + (par ^ 1) * 8 : s_tail + tid * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) head[i] = c2_add(head[i], tail_src[i]);
+        }
+        if (tid == last) s_ylastc[par] = head[B200_FM_OPT - 1];
+        else s_ylast[tid + 1] = head[B200_FM_OPT - 1];
+        __syncthreads(); /* S2 */
+
+        /* ---- discriminator + thread-serial de-emphasis ---- */
+        float e[B200_FM_OPT];
+        {
+            float pr, pi;
+            c2_get(tid == 0 ? s_ylastc[par ^ 1] : s_ylast[tid], pr, pi);
+            float d[B200_FM_OPT];
+#pragma unroll
+            for (int i = 0; i < B200_FM_OPT; ++i) {
+                float yr, yi;
+                c2_get(head[i], yr, yi);
+                float zr = fmaf(yr, pr, yi * pi);
+                float zi = fmaf(yi, pr, -(yr * pi));
+                d[i] = atan2f(zi, zr);
+                pr = yr;
+                pi = yi;
+            }
+            if (p.m_base + m0 == 0 && tid == 0) d[0] = 0.0f; /* y1[-1] = 0: defined as d[0] = 0 */
+            if (p.disc && store) {
+                const uint64_t m = m0 + (uint64_t)tid * B200_FM_OPT;
+                float *dst = p.disc + (uint64_t)capture * p.disc_stride + m;
+#pragma unroll
+                for (int i = 0; i < B200_FM_OPT; ++i)
+                    if (m + i < p.m1) dst[i] = d[i];
+            }
+            float run = 0.0f;
+#pragma unroll
+            for (int i = 0; i < B200_FM_OPT; ++i) {
+                run = fmaf(a1, run, alpha * d[i]);
+                e[i] = run;
+            }
+        }
+        /* warp scan of the chunk totals: v_l = sum_{l'<=l} (a^12)^(l-l') E11_l' */
+        float v = e[B200_FM_OPT - 1];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            float u = __shfl_up_sync(0xffffffffu, v, 1u << s);
+            if (lane >= (1 << s)) v = fmaf(taps->a12pow[s], u, v);
+        }
+        float vprev = __shfl_up_sync(0xffffffffu, v, 1u);
+        if (lane == 0) vprev = 0.0f;
+        if (lane == 31) s_wsum[warp] = v;
+        __syncthreads(); /* S3 */
+        {
+            float cw = s_wsum[4]; /* carry into warp 0 = e[m0-1] */
+            for (int w = 0; w < warp; ++w) cw = fmaf(taps->a384, cw, s_wsum[w]);
+            const float cin = fmaf(lane_pow, cw, vprev); /* e just before this thread's chunk */
+#pragma unroll
+            for (int i = 0; i < B200_FM_OPT; ++i) {
+                e[i] = fmaf(taps->apow[i], cin, e[i]);
+                s_e[B200_FM_HIST + tid * B200_FM_OPT + i] = e[i];
+            }
+        }
+        __syncthreads(); /* S4 */
+
+        /* ---- stage 2: audio[p] = sum_k h2[k] e[5 p - k] for 5 p in this tile ---- */
+        {
+            const uint64_t mg0 = p.m_base + m0;                   /* global stage-1 index of tile start */
+            const uint64_t pg_first = (mg0 + B200_FM_D2 - 1) / B200_FM_D2; /* first global audio index */
+            for (uint64_t pg = pg_first + (uint64_t)tid;; pg += B200_FM_THREADS) {
+                const uint64_t mg = pg * B200_FM_D2;
+                if (mg >= mg0 + B200_FM_TILE_OUT || mg - p.m_base >= p.m1) break;
+                const float *win = s_e + B200_FM_HIST + (int)(mg - mg0);
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < B200_FM_T2; ++k) s = fmaf(taps->h2[k], win[-k], s);
+                if (store) {
+                    const uint64_t pl = pg - p.audio_base; /* index into this launch's audio buffer */
+                    p.audio[(uint64_t)capture * p.audio_stride + pl] = s;
+                }
+            }
+        }
+        __syncthreads(); /* S5 */
+        /* e carries for the next tile (tails / ylast travel through the parity buffers) */
+        if (tid == 9) s_wsum[4] = s_e[B200_FM_HIST + (last + 1) * B200_FM_OPT - 1];
+        if (tid >= 32 && tid < 32 + B200_FM_HIST) s_e[tid - 32] = s_e[(last + 1) * B200_FM_OPT + tid - 32];
+        /* the next tile's S1..S3 order these writes before their readers */
+    }
+
+    if (p.state) {
+        __syncthreads();
+        const int fin = my_tiles ? (int)((my_tiles - 1) & 1) : 1; /* carry buffer written last */
+        if (tid < 8) {
+            float tr, ti;
+            c2_get(s_tailc[fin * 8 + tid], tr, ti);
+            p.state[capture].tail[2 * tid] = tr;
+            p.state[capture].tail[2 * tid + 1] = ti;
+        }
+        if (tid == 8) {
+            float yr, yi;
+            c2_get(s_ylastc[fin], yr, yi);
+            p.state[capture].ylast[0] = yr;
+            p.state[capture].ylast[1] = yi;
+        }
+        if (tid == 9) p.state[capture].e_last = s_wsum[4];
+        if (tid >= 32 && tid < 32 + B200_FM_HIST) p.state[capture].e_hist[tid - 32] = s_e[tid - 32];
+    }
+}
+
+#endif

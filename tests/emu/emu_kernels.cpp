@@ -1,0 +1,172 @@
+/*
+ * emu_kernels.cpp -- runs the product's kernel SOURCE (stm32f7-rtlsdr_b200/csrc/*.cuh) on the
+ * host under tests/emu/cuda_emu.h, so the CPU test-suite can check kernel index arithmetic
+ * against the oracle without a GPU.  TEST INFRASTRUCTURE ONLY -- not a product fallback.
+ * Built by tests/conftest.py:  g++ -O1 -shared -fPIC -o tests/emu/libemu_kernels.so
+ */
+#include "cuda_emu.h"
+
+#include <vector>
+
+#include "../../stm32f7-rtlsdr_b200/csrc/plan.h"
+
+extern "C" {
+
+/* mean / EMA spectrum of one or more captures through k_spectrum + k_spectrum_finalize */
+int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, const float *window,
+                 uint32_t frames_per_warp, int ema, float beta, float *out)
+{
+    uint32_t frames = (uint32_t)b200::spectrum_frames(len_each_bytes);
+    if (frames == 0) return -1;
+    std::vector<float2> tw(1024);
+    b200::fill_twiddles(tw.data());
+    uint32_t frames_per_cta = frames_per_warp * B200_SPEC_WARPS;
+    uint32_t ctas = (frames + frames_per_cta - 1) / frames_per_cta;
+    std::vector<float> partials((size_t)n_captures * ctas * 1024);
+    SpectrumParams p;
+    p.iq = iq;
+    p.capture_stride = len_each_bytes;
+    p.frames = frames;
+    p.frames_per_warp = frames_per_warp;
+    p.window = window;
+    p.twiddle = tw.data();
+    p.partials = partials.data();
+    p.ctas_per_capture = ctas;
+    p.ema_beta = beta;
+    p.ema_log2_decay = log2f(1.0f - beta);
+    if (ema) emu::launch(dim3(ctas, n_captures), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<true>(p); });
+    else emu::launch(dim3(ctas, n_captures), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<false>(p); });
+    float scale = ema ? 1.0f : 1.0f / (float)frames;
+    emu::launch(dim3(4, n_captures), dim3(256), 0,
+                [&] { k_spectrum_finalize(partials.data(), ctas, scale, nullptr, 0.0f, out); });
+    return (int)frames;
+}
+
+/* WBFM over whole captures; tiles_per_segment = 0 takes the product's plan.
+ * `iq` must be readable up to a multiple of 16 bytes (capture_bytes is rounded down to 16 like the
+ * batched API requires). */
+int emu_wbfm_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, uint32_t tiles_per_segment,
+                   float *audio, float *disc)
+{
+    b200::fill_fm_taps(c_fm_taps);
+    b200::FmPlan pl = b200::plan_wbfm_batch(len_each_bytes, n_captures, 148);
+    if (tiles_per_segment) {
+        pl.tiles_per_segment = tiles_per_segment;
+        pl.segments = (uint32_t)b200::ceil_div(pl.n_tiles, tiles_per_segment);
+    }
+    FmParams p{};
+    p.iq = iq;
+    p.capture_stride = len_each_bytes;
+    p.capture_bytes = len_each_bytes;
+    p.m1 = pl.m1;
+    p.m_base = 0;
+    p.n_tiles = pl.n_tiles;
+    p.total_chunks = pl.total_chunks;
+    p.tiles_per_segment = pl.tiles_per_segment;
+    p.audio = audio;
+    p.audio_stride = b200::wbfm_audio_len(len_each_bytes);
+    p.audio_base = 0;
+    p.disc = disc;
+    p.disc_stride = pl.m1;
+    p.state = nullptr;
+    p.n_audio_out = nullptr;
+    emu::launch(dim3(pl.segments, n_captures), dim3(B200_FM_THREADS), B200_FM_SMEM_BYTES, [&] { k_wbfm(p); });
+    return (int)pl.segments;
+}
+
+/* WBFM streaming step: `n_chunks` whole 120-sample chunks starting at stream chunk index
+ * `chunk_base`, exact state carried in *state (FmState, zero it before the first call). */
+int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, void *state, float *audio,
+                    uint32_t *n_audio, float *disc)
+{
+    b200::fill_fm_taps(c_fm_taps);
+    FmParams p{};
+    p.iq = iq;
+    p.capture_stride = 0;
+    p.capture_bytes = (uint64_t)n_chunks * 2 * B200_FM_CHUNK;
+    p.m1 = (uint64_t)n_chunks * B200_FM_OPT;
+    p.m_base = chunk_base * B200_FM_OPT;
+    p.total_chunks = n_chunks;
+    p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_FM_THREADS);
+    p.tiles_per_segment = p.n_tiles ? p.n_tiles : 1;
+    p.audio = audio;
+    p.audio_stride = 0;
+    p.audio_base = b200::ceil_div(p.m_base, B200_FM_D2);
+    p.disc = disc;
+    p.disc_stride = 0;
+    p.state = (FmState *)state;
+    emu::launch(dim3(1, 1), dim3(B200_FM_THREADS), B200_FM_SMEM_BYTES, [&] { k_wbfm(p); });
+    *n_audio = (uint32_t)(b200::ceil_div(p.m_base + p.m1, B200_FM_D2) - p.audio_base);
+    return 0;
+}
+
+int emu_sizeof_fm_state(void) { return (int)sizeof(FmState); }
+
+/* AM over whole captures: k_am_front (optionally segmented) + k_am_back */
+int emu_am_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, uint32_t tiles_per_segment,
+                 float *audio, float *env_out)
+{
+    b200::fill_am_taps(c_am_taps);
+    b200::AmPlan pl = b200::plan_am_batch(len_each_bytes, n_captures, 148);
+    if (tiles_per_segment) {
+        pl.tiles_per_segment = tiles_per_segment;
+        pl.segments = (uint32_t)b200::ceil_div(pl.n_tiles, tiles_per_segment);
+    }
+    std::vector<float> env((size_t)n_captures * pl.q_count);
+    AmFrontParams p{};
+    p.iq = iq;
+    p.capture_stride = len_each_bytes;
+    p.capture_bytes = len_each_bytes;
+    p.q_count = pl.q_count;
+    p.n_tiles = pl.n_tiles;
+    p.total_chunks = pl.total_chunks;
+    p.tiles_per_segment = pl.tiles_per_segment;
+    p.env = env.data();
+    p.env_stride = pl.q_count;
+    p.state = nullptr;
+    emu::launch(dim3(pl.segments, n_captures), dim3(B200_AM_THREADS), B200_AM_SMEM_BYTES, [&] { k_am_front(p); });
+    if (env_out) memcpy(env_out, env.data(), env.size() * sizeof(float));
+    AmBackParams b{};
+    b.env = env.data();
+    b.env_stride = pl.q_count;
+    b.q_count = pl.q_count;
+    b.q_base = 0;
+    b.audio = audio;
+    b.audio_stride = pl.audio_len;
+    b.audio_base = 0;
+    b.state = nullptr;
+    emu::launch(dim3(n_captures), dim3(B200_AMB_THREADS), 0, [&] { k_am_back(b); });
+    return (int)pl.segments;
+}
+
+/* AM streaming step over n_chunks whole 200-sample chunks starting at stream chunk `chunk_base` */
+int emu_am_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, void *fstate, void *bstate, float *audio,
+                  uint32_t *n_audio)
+{
+    b200::fill_am_taps(c_am_taps);
+    std::vector<float> env(n_chunks + 1);
+    AmFrontParams p{};
+    p.iq = iq;
+    p.capture_bytes = (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
+    p.q_count = n_chunks;
+    p.total_chunks = n_chunks;
+    p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_AM_THREADS);
+    p.tiles_per_segment = p.n_tiles ? p.n_tiles : 1;
+    p.env = env.data();
+    p.state = (AmFrontState *)fstate;
+    emu::launch(dim3(1, 1), dim3(B200_AM_THREADS), B200_AM_SMEM_BYTES, [&] { k_am_front(p); });
+    AmBackParams b{};
+    b.env = env.data();
+    b.q_count = n_chunks;
+    b.q_base = chunk_base;
+    b.audio = audio;
+    b.audio_base = (2 * chunk_base + 2) / 3;
+    b.state = (AmBackState *)bstate;
+    emu::launch(dim3(1), dim3(B200_AMB_THREADS), 0, [&] { k_am_back(b); });
+    *n_audio = (uint32_t)((2 * (chunk_base + n_chunks) + 2) / 3 - b.audio_base);
+    return 0;
+}
+int emu_sizeof_am_front_state(void) { return (int)sizeof(AmFrontState); }
+int emu_sizeof_am_back_state(void) { return (int)sizeof(AmBackState); }
+
+} /* extern "C" */
