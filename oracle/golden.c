@@ -410,7 +410,7 @@ void gold_synth_fill(uint8_t *iq, uint32_t n_captures, uint64_t len_each, uint32
  * FIFO copy (gold_ingest_copy in <=65024-byte URBs of 512-byte packets, USBH/Src/usbh_ioreq.c:220),
  * then processed.  Returns wall seconds (CLOCK_MONOTONIC). */
 typedef struct {
-    const uint8_t *iq; size_t n_each; uint32_t n_blocks; int tid, threads; int kind; real *out; size_t out_each;
+    const uint8_t *iq; size_t n_each; uint32_t n_distinct, n_blocks; int tid, threads; int kind; double checksum;
 } work_t;
 
 static void *worker(void *arg)
@@ -418,33 +418,38 @@ static void *worker(void *arg)
     work_t *w = (work_t *)arg;
     size_t bytes = 2 * w->n_each;
     uint8_t *buf = (uint8_t *)malloc(bytes + 8);
+    size_t out_len = GOLD_NFFT;
+    if (w->kind == 1) out_len = gold_wbfm_audio_len(w->n_each);
+    if (w->kind == 2) out_len = gold_am_audio_len(w->n_each);
+    real *o = (real *)malloc(sizeof(real) * (out_len + 1));
     for (uint32_t b = (uint32_t)w->tid; b < w->n_blocks; b += (uint32_t)w->threads) {
-        const uint8_t *src = w->iq + (size_t)b * bytes;
+        const uint8_t *src = w->iq + (size_t)(b % w->n_distinct) * bytes;
         for (size_t off = 0; off < bytes; off += 512) {
             size_t l = bytes - off < 512 ? bytes - off : 512;
             gold_ingest_copy(buf + off, src + off, (uint16_t)l);
         }
-        real *o = w->out + (size_t)b * w->out_each;
         if (w->kind == 0) gold_spectrum(buf, w->n_each, GOLD_WIN_HANN, GOLD_AVG_MEAN, 0.0, o);
         else if (w->kind == 1) gold_wbfm(buf, w->n_each, o, NULL);
         else gold_am(buf, w->n_each, o);
+        w->checksum += (double)o[out_len / 2];
     }
     free(buf);
+    free(o);
     return NULL;
 }
 
-static double run_timed(int kind, const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out,
-                        size_t out_each)
+static double run_timed(int kind, const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads)
 {
     if (threads < 1) threads = 1;
-    if (threads > 256) threads = 256;
-    pthread_t th[256];
-    work_t ws[256];
+    if (threads > 512) threads = 512;
+    if (n_distinct < 1) n_distinct = 1;
+    pthread_t th[512];
+    static work_t ws[512];
     get_plan(GOLD_NFFT);
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; ++t) {
-        ws[t] = (work_t){iq, n_each, n_blocks, t, threads, kind, out, out_each};
+        ws[t] = (work_t){iq, n_each, n_distinct, n_blocks, t, threads, kind, 0.0};
         pthread_create(&th[t], NULL, worker, &ws[t]);
     }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
@@ -452,15 +457,16 @@ static double run_timed(int kind, const uint8_t *iq, size_t n_each, uint32_t n_b
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
-double gold_time_spectrum(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out)
+/* `n_blocks` blocks of n_each complex samples are processed; block b reads buffer b % n_distinct */
+double gold_time_spectrum(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads)
 {
-    return run_timed(0, iq, n_each, n_blocks, threads, out, GOLD_NFFT);
+    return run_timed(0, iq, n_each, n_distinct, n_blocks, threads);
 }
-double gold_time_wbfm(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out)
+double gold_time_wbfm(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads)
 {
-    return run_timed(1, iq, n_each, n_blocks, threads, out, gold_wbfm_audio_len(n_each));
+    return run_timed(1, iq, n_each, n_distinct, n_blocks, threads);
 }
-double gold_time_am(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out)
+double gold_time_am(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads)
 {
-    return run_timed(2, iq, n_each, n_blocks, threads, out, gold_am_audio_len(n_each));
+    return run_timed(2, iq, n_each, n_distinct, n_blocks, threads);
 }

@@ -81,10 +81,11 @@ void gold_am(const uint8_t *iq, size_t n, real *audio);
 /* synthetic captures (include/b200sdr_synth.h), n_captures x len_each bytes */
 void gold_synth_fill(uint8_t *iq, uint32_t n_captures, uint64_t len_each, uint32_t kind, uint64_t first_capture);
 
-/* ---- CPU baseline timing helpers (run `reps` times over distinct blocks, return seconds) ---- */
-double gold_time_spectrum(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *out1024_each);
-double gold_time_wbfm(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *audio_each);
-double gold_time_am(const uint8_t *iq, size_t n_each, uint32_t n_blocks, int threads, real *audio_each);
+/* ---- CPU baseline timing helpers: n_blocks blocks of n_each complex samples (block b reads
+ * distinct buffer b % n_distinct) over `threads` POSIX threads; returns wall seconds ---- */
+double gold_time_spectrum(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads);
+double gold_time_wbfm(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads);
+double gold_time_am(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads);
 
 #ifdef __cplusplus
 }

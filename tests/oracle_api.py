@@ -40,7 +40,7 @@ def _load(name):
     lib.gold_synth_fill.argtypes = [vp, u32, u64, u32, u64]
     for f in ("gold_time_spectrum", "gold_time_wbfm", "gold_time_am"):
         getattr(lib, f).restype = C.c_double
-        getattr(lib, f).argtypes = [vp, sz, u32, C.c_int, vp]
+        getattr(lib, f).argtypes = [vp, sz, u32, u32, C.c_int]
     return lib
 
 

@@ -1,0 +1,363 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libb200sdr.so), against the
+oracles on the same seeded inputs.  Run on the B200 box: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star):
+  * u8 -> cf32 conversion, ingest bytes, block indexing: BIT-EXACT
+  * spectrum power: <= 1e-5 relative error per bin
+  * discriminator: <= 1e-4 rad (compared modulo 2 pi); audio: <= 1e-4 x gain
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_api import (AVG_EMA, SYNTH_AM, SYNTH_COUNTER, SYNTH_MULTITONE, SYNTH_WBFM, WIN_BLACKMAN, WIN_HANN,
+                        WIN_RECT, Golden, RefHost, wrap_phase)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SPEC_RTOL = 1e-5      # relative, per bin
+DISC_ATOL = 1e-4      # radians
+FM_AUDIO_ATOL = 1e-4 * 240000.0 / (2 * np.pi * 75000.0)
+AM_AUDIO_ATOL = 1e-6  # AM audio is O(0.05); fp32 FIRs give ~1e-8
+
+
+@pytest.fixture(scope="module")
+def g():
+    return Golden()
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def sdr(sdr_lib):
+    s = sdr_lib.B200Sdr()
+    yield s
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------ K2
+def test_convert_bit_exact_all_bytes(sdr, g, vec):
+    iq = np.arange(256, dtype=np.uint8)
+    out = sdr.convert_cf32(iq)
+    assert out.dtype == np.float32
+    assert np.array_equal(out.astype(np.float64), vec["convert_all_bytes"])  # exact: u - 127.5
+
+
+@pytest.mark.parametrize("nbytes", [4, 12, 16, 1020, 262144])
+def test_convert_bit_exact_ragged(sdr, g, nbytes):
+    iq = np.random.default_rng(nbytes).integers(0, 256, nbytes, dtype=np.uint8)
+    assert np.array_equal(sdr.convert_cf32(iq).astype(np.float64), g.convert(iq))
+
+
+@pytest.mark.parametrize("window", [WIN_HANN, WIN_BLACKMAN])
+def test_convert_windowed(sdr, sdr_lib, g, window):
+    iq = g.synth(1, 8192, SYNTH_MULTITONE, 1)
+    out = sdr.convert_cf32(iq, window=window)
+    # device window is the float32 rounding of the golden window; product is one fp32 multiply
+    w32 = g.window(window).astype(np.float32)
+    assert np.array_equal(sdr.get_window(window), w32)
+    expect = (g.convert(iq).astype(np.float32).reshape(-1, 2) * np.tile(w32, 4)[: iq.size // 2, None]).reshape(-1)
+    assert np.array_equal(out, expect)  # bit-exact against the same fp32 multiply
+    assert np.max(np.abs(out - g.convert(iq, window=window))) <= 128 * 2.0 ** -23
+
+
+def test_taps_match_oracle(sdr, g):
+    for which in range(5):
+        assert np.array_equal(sdr.get_taps(which), g.taps(which).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------ spectrum
+def spec_check(out, gold, rtol=SPEC_RTOL):
+    rel = np.abs(out.astype(np.float64) - gold) / gold
+    assert rel.max() <= rtol, f"max rel err {rel.max():.3e} at bin {rel.argmax()}"
+
+
+def test_spectrum_config0_block(sdr, g):
+    """BASELINE config[0]: one 256 KiB block -> 1024-pt Hann FFT power spectrum (255 frames)."""
+    iq = g.synth(1, 262144, SYNTH_MULTITONE, 0)
+    out = sdr.spectrum(iq)
+    gold, frames = g.spectrum(iq)
+    assert frames == 255
+    spec_check(out[0], gold)
+
+
+def test_spectrum_golden_fixture(sdr, sdr_lib, vec):
+    iq = sdr_lib.synth_fill_host(1, int(vec["spec_len"]), SYNTH_MULTITONE, int(vec["spec_seed"]))
+    spec_check(sdr.spectrum(iq)[0], vec["spec_hann_mean"], rtol=3e-5)  # only 15 frames averaged
+
+
+@pytest.mark.parametrize("n_captures,len_each", [(1, 2048), (3, 2048 + 1024 * 7 + 16), (5, 262144), (2, 4 * 262144)])
+def test_spectrum_batches(sdr, g, n_captures, len_each):
+    iq = g.synth(n_captures, len_each, SYNTH_MULTITONE, 40)
+    out = sdr.spectrum(iq, n_captures)
+    for c in range(n_captures):
+        gold, frames = g.spectrum(iq[c * len_each:(c + 1) * len_each])
+        spec_check(out[c], gold, rtol=SPEC_RTOL if frames >= 200 else 5e-5)
+
+
+def test_spectrum_short_capture_is_zero(sdr):
+    assert not sdr.spectrum(np.zeros(2032, np.uint8)).any()  # < 1024 samples: no frame
+
+
+def test_spectrum_random_bytes(sdr, g):
+    iq = np.random.default_rng(0).integers(0, 256, 262144, dtype=np.uint8)
+    spec_check(sdr.spectrum(iq)[0], g.spectrum(iq)[0])
+
+
+def test_spectrum_extreme_bytes(sdr, g):
+    iq = np.zeros(65536, np.uint8)
+    iq[::3] = 255  # full-scale square-ish pattern: largest magnitudes the FFT can see
+    out, gold = sdr.spectrum(iq)[0].astype(np.float64), g.spectrum(iq)[0]
+    assert np.max(np.abs(out - gold)) <= 1e-5 * gold.max()
+
+
+@pytest.mark.parametrize("window", [WIN_RECT, WIN_BLACKMAN])
+def test_spectrum_other_windows(sdr_lib, g, window):
+    iq = g.synth(1, 262144, SYNTH_MULTITONE, 3)
+    with sdr_lib.B200Sdr(window=window) as s:
+        out = s.spectrum(iq)[0].astype(np.float64)
+    gold = g.spectrum(iq, window=window)[0]
+    assert np.max(np.abs(out - gold) / np.maximum(gold, 1e-7 * gold.max())) <= 1e-5
+
+
+def test_spectrum_ema(sdr_lib, g):
+    iq = g.synth(1, 262144, SYNTH_MULTITONE, 4)
+    with sdr_lib.B200Sdr(avg_mode=AVG_EMA, ema_beta=0.1) as s:
+        out = s.spectrum(iq)[0]
+    spec_check(out, g.spectrum(iq, avg_mode=AVG_EMA, beta=0.1)[0], rtol=5e-5)  # ~20 effective frames
+
+
+def test_spectrum_parseval(sdr, g):
+    """Size-independent property: sum_k P[k] = 1024 * mean_m sum_n |w[n] x_m[n]|^2."""
+    iq = g.synth(1, 2 * 262144, SYNTH_MULTITONE, 8)
+    P = sdr.spectrum(iq)[0].astype(np.float64)
+    x = g.convert(iq).reshape(-1, 2)
+    x = x[:, 0] + 1j * x[:, 1]
+    w = g.window(WIN_HANN)
+    frames = (x.size - 1024) // 512 + 1
+    e = np.mean([np.sum(np.abs(x[512 * m:512 * m + 1024] * w) ** 2) for m in range(frames)])
+    assert abs(P.sum() - 1024 * e) <= 1e-6 * 1024 * e
+
+
+# ---------------------------------------------------------------------------------------- WBFM
+def test_wbfm_golden_fixture(sdr, sdr_lib, vec):
+    iq = sdr_lib.synth_fill_host(1, int(vec["fm_len"]), SYNTH_WBFM, int(vec["fm_seed"]))
+    audio, disc = sdr.wbfm(iq, want_disc=True)
+    assert np.max(np.abs(wrap_phase(disc[0] - vec["fm_disc"]))) <= DISC_ATOL
+    assert np.max(np.abs(audio[0] - vec["fm_audio"])) <= FM_AUDIO_ATOL
+
+
+@pytest.mark.parametrize("n_captures,len_each", [(1, 16), (1, 2416), (2, 262144), (3, 30720 * 5 + 240 * 3 + 16), (1, 4800000)])
+def test_wbfm_batches(sdr, g, n_captures, len_each):
+    iq = g.synth(n_captures, len_each, SYNTH_WBFM, 50)
+    audio, disc = sdr.wbfm(iq, n_captures, want_disc=True)
+    for c in range(n_captures):
+        ga, gd = g.wbfm(iq[c * len_each:(c + 1) * len_each], want_disc=True)
+        assert audio[c].size == ga.size and disc[c].size == gd.size
+        assert np.max(np.abs(wrap_phase(disc[c] - gd))) <= DISC_ATOL
+        assert np.max(np.abs(audio[c] - ga)) <= FM_AUDIO_ATOL
+
+
+def test_wbfm_host_path_equals_device_path(sdr, g):
+    iq = g.synth(4, 262144, SYNTH_WBFM, 60)
+    a_host = sdr.wbfm(iq, 4)
+    a_dev, _ = sdr.wbfm(iq, 4, want_disc=True)
+    assert np.array_equal(a_host, a_dev)
+
+
+# ------------------------------------------------------------------------------------------ AM
+def test_am_golden_fixture(sdr, sdr_lib, vec):
+    iq = sdr_lib.synth_fill_host(1, int(vec["am_len"]), SYNTH_AM, int(vec["am_seed"]))
+    assert np.max(np.abs(sdr.am(iq)[0] - vec["am_audio"])) <= AM_AUDIO_ATOL
+
+
+@pytest.mark.parametrize("n_captures,len_each", [(1, 16), (1, 4816), (2, 262144), (2, 51200 * 3 + 400 * 7 + 32), (1, 4800000)])
+def test_am_batches(sdr, g, n_captures, len_each):
+    iq = g.synth(n_captures, len_each, SYNTH_AM, 70)
+    audio = sdr.am(iq, n_captures)
+    for c in range(n_captures):
+        ga = g.am(iq[c * len_each:(c + 1) * len_each])
+        assert audio[c].size == ga.size
+        assert np.max(np.abs(audio[c] - ga)) <= AM_AUDIO_ATOL
+
+
+# ----------------------------------------------------------------------------------- streaming
+def feed(s, iq, cuts):
+    pos = 0
+    for n in cuts:
+        rc = s.process_samples(iq[pos:pos + n], allow_busy=True)
+        while rc == 1:  # B200SDR_BUSY: ring full -> call again (cooperative, like USBH_BUSY)
+            s.sync()
+            rc = s.process_samples(iq[pos:pos + n], allow_busy=True)
+        pos += n
+    assert pos == iq.size
+
+
+def random_cuts(total, max_block, seed):
+    rng = np.random.default_rng(seed)
+    cuts, left = [], total
+    while left:
+        n = int(min(left, 4 * rng.integers(1, max_block // 4 + 1)))
+        cuts.append(n)
+        left -= n
+    return cuts
+
+
+@pytest.mark.parametrize("cuts_kind", ["baseline_blocks", "reference_512", "random"])
+def test_streaming_all_chains_block_cut_invariance(sdr_lib, g, cuts_kind):
+    """A stream cut into blocks at arbitrary 4-byte boundaries gives the single-capture result."""
+    total = 262144 * 3 + 512 * 5
+    iq = g.synth(1, total, SYNTH_WBFM, 90)
+    cuts = {"baseline_blocks": [262144] * 3 + [512 * 5], "reference_512": [512] * (total // 512),
+            "random": random_cuts(total, 65536, 7)}[cuts_kind]
+    with sdr_lib.B200Sdr(slot_bytes=262144, ring_slots=4) as s:
+        feed(s, iq, cuts)
+        spec, frames = s.get_spectrum()
+        fm = s.get_audio(sdr_lib.CHAIN_WBFM)
+        am = s.get_audio(sdr_lib.CHAIN_AM)
+        cnt = s.counters()
+    assert cnt["bytes_in"] == total and cnt["blocks_in"] == len(cuts)
+    gold_spec, gold_frames = g.spectrum(iq)
+    assert frames == gold_frames
+    spec_check(spec, gold_spec)
+    # audio produced so far = every output whose chunk is complete
+    ga = g.wbfm(iq)
+    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    assert fm.size == n_fm and np.max(np.abs(fm - ga[:n_fm])) <= FM_AUDIO_ATOL
+    gam = g.am(iq)
+    n_am = (2 * (total // 2 // 200) + 2) // 3
+    assert am.size == n_am and np.max(np.abs(am - gam[:n_am])) <= AM_AUDIO_ATOL
+
+
+def test_streaming_reset_starts_a_new_capture(sdr_lib, g):
+    iq = g.synth(1, 262144, SYNTH_MULTITONE, 91)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        s.process_samples(np.random.default_rng(1).integers(0, 256, 8192, dtype=np.uint8))
+        s.reset()
+        s.process_samples(iq)
+        spec, frames = s.get_spectrum()
+    assert frames == 255
+    spec_check(spec, g.spectrum(iq)[0])
+
+
+def test_streaming_ema_spectrum(sdr_lib, g):
+    iq = g.synth(1, 262144 * 2, SYNTH_MULTITONE, 92)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM, avg_mode=AVG_EMA, ema_beta=0.1) as s:
+        feed(s, iq, random_cuts(iq.size, 32768, 3))
+        spec, _ = s.get_spectrum()
+    spec_check(spec, g.spectrum(iq, avg_mode=AVG_EMA, beta=0.1)[0], rtol=5e-5)
+
+
+# -------------------------------------------------------------------------------------- ingest
+def test_ingest_bytes_match_reference_copy(sdr_lib, g, tmp_path):
+    """Row a1-a7: the block that reaches the device is byte-identical to what the reference's own
+    FSM + IRQ copy leaves in CommItf.buff for the same stream (oracle A), block by block."""
+    ref = RefHost()
+    data = g.synth(1, 512 * 6, SYNTH_COUNTER, 0)
+    with sdr_lib.B200Sdr(slot_bytes=512, ring_slots=2, chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        for b in range(6):
+            blk = data[512 * b:512 * (b + 1)]
+            while s.process_samples(blk, allow_busy=True) == 1:
+                s.sync()
+            got, n = s.debug_last_block(512)
+            assert n == 512 and np.array_equal(got, blk)
+            if ref.available:
+                dest, written = ref.read_packet(blk, 512)
+                assert written == 512 and np.array_equal(dest[:512], got)
+        assert s.counters() == {"bytes_in": 3072, "blocks_in": 6, "busy_returns": s.counters()["busy_returns"]}
+    if ref.available:
+        out, _ = ref.run_stream(data, 512, 7, str(tmp_path))
+        assert np.array_equal(out, data)
+
+
+def test_ring_acquire_commit_zero_copy(sdr_lib, g):
+    iq = g.synth(1, 262144, SYNTH_MULTITONE, 93)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        slot = s.ring_acquire()
+        assert slot is not None and slot.size == 262144
+        slot[:] = iq
+        s.ring_commit(iq.size)
+        spec, frames = s.get_spectrum()
+    assert frames == 255
+    spec_check(spec, g.spectrum(iq)[0])
+
+
+def test_error_behaviour(sdr_lib):
+    with sdr_lib.B200Sdr(slot_bytes=4096, ring_slots=2) as s:
+        assert s.process_samples_raw(np.zeros(6, np.uint8)) == sdr_lib.NOT_SUPPORTED     # multiple-of-4 rule
+        assert s.process_samples_raw(np.zeros(8192, np.uint8)) == sdr_lib.NOT_SUPPORTED  # larger than a slot
+        assert s.process_samples_raw(np.zeros(0, np.uint8)) == sdr_lib.OK
+        assert s.process_samples_raw(np.zeros(4096, np.uint8)) == sdr_lib.OK
+    with pytest.raises(sdr_lib.B200SdrError) as ei:
+        sdr_lib.B200Sdr(slot_bytes=510)
+    assert ei.value.status == sdr_lib.NOT_SUPPORTED
+    with pytest.raises(sdr_lib.B200SdrError):
+        sdr_lib.B200Sdr(ring_slots=1)
+
+
+def test_busy_when_ring_is_full(sdr_lib):
+    """USBH_BUSY semantics: with every slot in flight the call returns BUSY and must be retried."""
+    blk = np.zeros(1 << 22, np.uint8)
+    with sdr_lib.B200Sdr(slot_bytes=1 << 22, ring_slots=2, chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        codes = [s.process_samples(blk, allow_busy=True) for _ in range(64)]
+        s.sync()
+        assert set(codes) <= {0, 1}
+        assert s.counters()["blocks_in"] == codes.count(0)
+        assert s.counters()["busy_returns"] == codes.count(1)
+
+
+# ------------------------------------------------------------------- device generator + full size
+@pytest.mark.parametrize("kind", [SYNTH_COUNTER, SYNTH_MULTITONE, SYNTH_WBFM, SYNTH_AM])
+def test_device_generator_bit_identical(sdr, g, kind):
+    n_cap, len_each = 3, 65536
+    d = sdr.dev_alloc(n_cap * len_each)
+    try:
+        sdr.synth_fill_dev(d, n_cap, len_each, kind, first_capture=17)
+        sdr.sync()
+        got = sdr.to_host(d, n_cap * len_each)
+    finally:
+        sdr.dev_free(d)
+    assert np.array_equal(got, g.synth(n_cap, len_each, kind, first_capture=17))
+
+
+def test_full_size_capture_batch(sdr, g):
+    """BASELINE configs[1..3] at full size: 10 s captures (48 MB each) generated on the device,
+    run resident in HBM; captures picked from the batch are re-generated on the CPU and checked
+    against the golden model; equal-seed captures give bitwise equal outputs."""
+    n_cap, len_each = 6, 48_000_000
+    d_iq = sdr.dev_alloc(n_cap * len_each)
+    na, nam = 480000, 80000
+    d_spec, d_fm, d_am = sdr.dev_alloc(4 * 1024 * n_cap), sdr.dev_alloc(4 * na * n_cap), sdr.dev_alloc(4 * nam * n_cap)
+    try:
+        # captures 0,1: multitone; 2,3: WBFM; 4,5: AM -- and capture 1/3/5 repeat seeds of 0/2/4
+        for c, kind, seed in [(0, SYNTH_MULTITONE, 1000), (1, SYNTH_MULTITONE, 1000), (2, SYNTH_WBFM, 1001),
+                              (3, SYNTH_WBFM, 1001), (4, SYNTH_AM, 1002), (5, SYNTH_AM, 1002)]:
+            sdr.synth_fill_dev(d_iq + c * len_each, 1, len_each, kind, first_capture=seed)
+        sdr.batch_spectrum_dev(d_iq, n_cap, len_each, d_spec)
+        sdr.batch_wbfm_dev(d_iq, n_cap, len_each, d_fm)
+        sdr.batch_am_dev(d_iq, n_cap, len_each, d_am)
+        sdr.sync()
+        spec = sdr.to_host(d_spec, 4 * 1024 * n_cap, np.float32).reshape(n_cap, 1024)
+        fm = sdr.to_host(d_fm, 4 * na * n_cap, np.float32).reshape(n_cap, na)
+        am = sdr.to_host(d_am, 4 * nam * n_cap, np.float32).reshape(n_cap, nam)
+    finally:
+        for p in (d_iq, d_spec, d_fm, d_am):
+            sdr.dev_free(p)
+    for a in (spec, fm, am):
+        assert np.array_equal(a[0], a[1]) and np.array_equal(a[2], a[3]) and np.array_equal(a[4], a[5])
+    gold, frames = g.spectrum(g.synth(1, len_each, SYNTH_MULTITONE, 1000))
+    assert frames == 46874
+    spec_check(spec[0], gold)
+    assert np.max(np.abs(fm[2] - g.wbfm(g.synth(1, len_each, SYNTH_WBFM, 1001)))) <= FM_AUDIO_ATOL
+    assert np.max(np.abs(am[4] - g.am(g.synth(1, len_each, SYNTH_AM, 1002)))) <= AM_AUDIO_ATOL
+
+
+def test_kernel_launch_counter_moves(sdr, g):
+    before = sdr.kernel_launches()
+    sdr.spectrum(g.synth(1, 262144, SYNTH_MULTITONE, 0))
+    assert sdr.kernel_launches() >= before + 2
