@@ -28,7 +28,7 @@ namespace {
 constexpr uint32_t kCarryMax = 2048;         /* spectrum carry: < 1024 samples                    */
 constexpr uint32_t kFmLeftMax = 240;         /* < one 120-sample chunk                            */
 constexpr uint32_t kAmLeftMax = 400;         /* < one 200-sample chunk                            */
-constexpr uint64_t kWaveBytesDefault = 384ull << 20;
+constexpr uint64_t kWaveBytesDefault = 192ull << 20;
 
 struct AudioFifo {
     float *d_buf = nullptr;   /* device FIFO storage (linear, compacted on pop)                    */

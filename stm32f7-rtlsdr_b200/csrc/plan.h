@@ -60,11 +60,11 @@ inline FmPlan plan_wbfm_batch(uint64_t len_bytes, uint32_t n_captures, uint32_t 
     pl.m1 = ceil_div(n, 10);
     pl.total_chunks = (uint32_t)ceil_div(n, B200_FM_CHUNK);
     pl.n_tiles = (uint32_t)ceil_div(pl.total_chunks, B200_FM_THREADS);
-    /* enough segments for ~6 CTAs per SM over the batch, but segments of >= 8 tiles so the
-     * one-tile pre-roll of segments > 0 stays a small overhead */
-    uint64_t want = ceil_div((uint64_t)sm_count * 6, n_captures ? n_captures : 1);
+    /* many equal segments (>= ~10 waves of CTAs at 4 CTAs per SM, so the last partial wave is
+     * small) but never shorter than 16 tiles: segments > 0 re-run one tile as pre-roll */
+    uint64_t want = ceil_div((uint64_t)sm_count * 40, n_captures ? n_captures : 1);
     uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
-    if (tps < 8) tps = 8;
+    if (tps < 16) tps = 16;
     if (tps > pl.n_tiles) tps = pl.n_tiles ? pl.n_tiles : 1;
     pl.tiles_per_segment = (uint32_t)tps;
     pl.segments = (uint32_t)ceil_div(pl.n_tiles, tps);
@@ -99,9 +99,9 @@ inline AmPlan plan_am_batch(uint64_t len_bytes, uint32_t n_captures, uint32_t sm
     pl.audio_len = am_audio_len(len_bytes);
     pl.total_chunks = (uint32_t)ceil_div(n, B200_AM_CHUNK);
     pl.n_tiles = (uint32_t)ceil_div(pl.total_chunks, B200_AM_THREADS);
-    uint64_t want = ceil_div((uint64_t)sm_count * 6, n_captures ? n_captures : 1);
+    uint64_t want = ceil_div((uint64_t)sm_count * 30, n_captures ? n_captures : 1);
     uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
-    if (tps < 8) tps = 8;
+    if (tps < 16) tps = 16;
     if (tps > pl.n_tiles) tps = pl.n_tiles ? pl.n_tiles : 1;
     pl.tiles_per_segment = (uint32_t)tps;
     pl.segments = (uint32_t)ceil_div(pl.n_tiles, tps);

@@ -94,10 +94,17 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, 3) k_spectrum(SpectrumParam
     const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
     const float *my_win = s_win + lane * B200_SPEC_WP;
 
+    /* software pipeline: the 32 two-byte loads of frame m+1 are issued before the FFT of frame m,
+     * so no warp ever waits on HBM/L2 latency with only three warps per scheduler resident */
+    const unsigned short *src0 = reinterpret_cast<const unsigned short *>(cap) + (uint32_t)lane;
+    uint32_t raw[32];
+    if (m_begin < m_end) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m_begin * 512u + 32 * j);
+    }
     for (uint32_t m = m_begin; m < m_end; ++m) {
-        const unsigned short *src = reinterpret_cast<const unsigned short *>(cap) + ((uint64_t)m * 512u + (uint32_t)lane);
         c2 v[32];
-        /* load + convert + window, written to the bit-reversed slot pass 1 wants */
+        /* convert + window, written to the bit-reversed slot pass 1 wants */
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * j4);
@@ -105,9 +112,13 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, 3) k_spectrum(SpectrumParam
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * j4 + jj;
-                uint32_t raw = (uint32_t)__ldg(src + 32 * j);
-                v[b200_bitrev5(j)] = c2_scale(c2_from_u8_lo(raw), wj[jj]);
+                v[b200_bitrev5(j)] = c2_scale(c2_from_u8_lo(raw[j]), wj[jj]);
             }
+        }
+        if (m + 1 < m_end) {
+            const unsigned short *src = src0 + (uint64_t)(m + 1) * 512u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src + 32 * j);
         }
         b200_fft32(v); /* v[k1] = Y[k1] */
 #pragma unroll

@@ -45,21 +45,25 @@
 #define B200_FM_TILE_IN (B200_FM_THREADS * B200_FM_CHUNK)  /* 15360                                  */
 #define B200_FM_TILE_OUT (B200_FM_THREADS * B200_FM_OPT)   /* 1536                                   */
 #define B200_FM_TILE_BYTES (2 * B200_FM_TILE_IN)           /* 30720                                  */
-#define B200_FM_STAGES 2
 #define B200_FM_T1 80
 #define B200_FM_T2 50
 #define B200_FM_D2 5
 #define B200_FM_HIST (B200_FM_T2 - 1) /* 49 */
+#define B200_FM_HPAD 52               /* history slots before the tile's e[] (16-byte aligned)        */
+#define B200_FM_TAILP 132             /* pitch (in c2) of one row of the transposed tail exchange     */
+#define B200_FM_APT 3                 /* consecutive audio samples per thread in stage 2              */
 
-/* shared memory carve-up */
+/* shared memory carve-up.  ONE raw buffer: the TMA copy of tile t+1 is issued as soon as the
+ * scatter FIR of tile t has consumed it and lands while the 240 kS/s stages run, so four CTAs
+ * fit on an SM and hide each other's barriers. */
 #define B200_FM_SM_RAW 0
-#define B200_FM_SM_TAIL (B200_FM_SM_RAW + B200_FM_STAGES * B200_FM_TILE_BYTES)         /* c2 [129][8]  */
-#define B200_FM_SM_YLAST (B200_FM_SM_TAIL + (B200_FM_THREADS + 1) * 8 * 8)             /* c2 [129]     */
-#define B200_FM_SM_E (B200_FM_SM_YLAST + (B200_FM_THREADS + 1) * 8)                    /* float [49+1536] */
-#define B200_FM_SM_WSUM (B200_FM_SM_E + (B200_FM_HIST + B200_FM_TILE_OUT + 3) / 4 * 16) /* float [8]    */
-#define B200_FM_SM_TAILC (B200_FM_SM_WSUM + 32)                                         /* c2 [2][8]    */
-#define B200_FM_SM_YLASTC (B200_FM_SM_TAILC + 2 * 8 * 8)                                /* c2 [2]       */
-#define B200_FM_SM_BAR (B200_FM_SM_YLASTC + 16)                                         /* u64 [2]      */
+#define B200_FM_SM_TAIL (B200_FM_SM_RAW + B200_FM_TILE_BYTES)                           /* c2 [8][132]      */
+#define B200_FM_SM_YLAST (B200_FM_SM_TAIL + 8 * B200_FM_TAILP * 8)                      /* c2 [129]         */
+#define B200_FM_SM_E (B200_FM_SM_YLAST + (B200_FM_THREADS + 4) * 8)                     /* float [52+1536+16] */
+#define B200_FM_SM_WSUM (B200_FM_SM_E + (B200_FM_HPAD + B200_FM_TILE_OUT + 16) * 4)     /* float [8]        */
+#define B200_FM_SM_TAILC (B200_FM_SM_WSUM + 32)                                         /* c2 [2][8]        */
+#define B200_FM_SM_YLASTC (B200_FM_SM_TAILC + 2 * 8 * 8)                                /* c2 [2]           */
+#define B200_FM_SM_BAR (B200_FM_SM_YLASTC + 16)                                         /* u64              */
 #define B200_FM_SMEM_BYTES (B200_FM_SM_BAR + 16)
 
 #ifndef B200_DYN_SMEM
@@ -149,7 +153,29 @@ static FmTaps c_fm_taps;
 __constant__ FmTaps c_fm_taps;
 #endif
 
-__global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
+/* atan2(y, x), branch-free, ~1.3e-7 rad: one MUFU.RCP, a degree-15 odd minimax polynomial on
+ * [0, 1] (fitted offline against float64 atan), then octant fix-ups.  atan2(0, 0) = 0. */
+B200_DEV float b200_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+    const float a = mn * __frcp_rn(mx);
+    const float s = a * a;
+    float p = -4.054550054e-03f;
+    p = fmaf(p, s, 2.186289528e-02f);
+    p = fmaf(p, s, -5.591223568e-02f);
+    p = fmaf(p, s, 9.642190620e-02f);
+    p = fmaf(p, s, -1.390862694e-01f);
+    p = fmaf(p, s, 1.994656515e-01f);
+    p = fmaf(p, s, -3.332986075e-01f);
+    p = fmaf(p, s, 9.999993356e-01f);
+    float r = p * a;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.0f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
+__global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
 {
     const FmTaps *taps = &c_fm_taps;
     B200_DYN_SMEM(smem);
@@ -196,7 +222,8 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
         s_ylastc[1] = c2_make(yr, yi);
     }
     if (tid == 9) s_wsum[4] = p.state ? p.state[capture].e_last : 0.0f; /* tile carry e[m0-1] */
-    if (tid >= 32 && tid < 32 + B200_FM_HIST) s_e[tid - 32] = p.state ? p.state[capture].e_hist[tid - 32] : 0.0f;
+    if (tid >= 32 && tid < 32 + B200_FM_HIST)
+        s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32] = p.state ? p.state[capture].e_hist[tid - 32] : 0.0f;
 
     auto issue_tile = [&](uint32_t it) { /* thread 0 only */
         const uint32_t tile = t_begin + it;
@@ -204,16 +231,13 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
         uint64_t bytes = p.capture_bytes > off ? p.capture_bytes - off : 0;
         if (bytes > B200_FM_TILE_BYTES) bytes = B200_FM_TILE_BYTES;
         bytes &= ~(uint64_t)15;
-        uint64_t *bar = s_bar + (it & 1);
-        b200_mbar_expect_tx(bar, (uint32_t)bytes);
-        if (bytes) b200_tma_load_1d(smem + B200_FM_SM_RAW + (it & 1) * B200_FM_TILE_BYTES, cap + off, (uint32_t)bytes, bar);
+        b200_mbar_expect_tx(s_bar, (uint32_t)bytes);
+        if (bytes) b200_tma_load_1d(smem + B200_FM_SM_RAW, cap + off, (uint32_t)bytes, s_bar);
     };
     if (tid == 0) {
-        b200_mbar_init(s_bar + 0, 1);
-        b200_mbar_init(s_bar + 1, 1);
+        b200_mbar_init(s_bar, 1);
         b200_mbar_fence_init();
         if (my_tiles > 0) issue_tile(0);
-        if (my_tiles > 1) issue_tile(1);
     }
     __syncthreads();
 
@@ -227,25 +251,29 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
         const int par = (int)(it & 1);
 
         /* ---- stage 1: scatter FIR over this thread's 120 samples ---- */
-        b200_mbar_wait(s_bar + (it & 1), (it >> 1) & 1);
+        b200_mbar_wait(s_bar, it & 1);
         c2 acc[8], head[B200_FM_OPT];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = c2_zero();
-        const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_FM_SM_RAW + (it & 1) * B200_FM_TILE_BYTES +
-                                                           tid * (2 * B200_FM_CHUNK));
+        const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_FM_SM_RAW + tid * (2 * B200_FM_CHUNK));
         b200_fm_words<0>::run(raw, h, acc, head);
-        /* tails: outputs 12..19 live in acc[i & 7] -> next thread's slots 0..7 */
-        {
-            c2 *tail_dst = (tid == last) ? s_tailc + par * 8 : s_tail + (tid + 1) * 8;
+        /* tails: outputs 12..19 live in acc[i & 7] -> next thread's heads 0..7.
+         * exchange tile is [i][thread] so a warp's stores / loads are contiguous */
+        if (tid == last) {
 #pragma unroll
-            for (int i = 12; i < 20; ++i) tail_dst[i - 12] = acc[i & 7];
+            for (int i = 12; i < 20; ++i) s_tailc[par * 8 + (i - 12)] = acc[i & 7];
+        } else {
+#pragma unroll
+            for (int i = 12; i < 20; ++i) s_tail[(i - 12) * B200_FM_TAILP + tid + 1] = acc[i & 7];
         }
         __syncthreads(); /* S1: raw buffer consumed, tails visible */
-        if (tid == 0 && it + 2 < my_tiles) issue_tile(it + 2);
-        {
-            const c2 *tail_src = (tid == 0) ? s_tailc + (par ^ 1) * 8 : s_tail + tid * 8;
+        if (tid == 0 && it + 1 < my_tiles) issue_tile(it + 1);
+        if (tid == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) head[i] = c2_add(head[i], tail_src[i]);
+            for (int i = 0; i < 8; ++i) head[i] = c2_add(head[i], s_tailc[(par ^ 1) * 8 + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) head[i] = c2_add(head[i], s_tail[i * B200_FM_TAILP + tid]);
         }
         if (tid == last) s_ylastc[par] = head[B200_FM_OPT - 1];
         else s_ylast[tid + 1] = head[B200_FM_OPT - 1];
@@ -263,7 +291,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
                 c2_get(head[i], yr, yi);
                 float zr = fmaf(yr, pr, yi * pi);
                 float zi = fmaf(yi, pr, -(yr * pi));
-                d[i] = atan2f(zi, zr);
+                d[i] = b200_atan2(zi, zr);
                 pr = yr;
                 pi = yi;
             }
@@ -298,34 +326,48 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
             for (int w = 0; w < warp; ++w) cw = fmaf(taps->a384, cw, s_wsum[w]);
             const float cin = fmaf(lane_pow, cw, vprev); /* e just before this thread's chunk */
 #pragma unroll
-            for (int i = 0; i < B200_FM_OPT; ++i) {
-                e[i] = fmaf(taps->apow[i], cin, e[i]);
-                s_e[B200_FM_HIST + tid * B200_FM_OPT + i] = e[i];
-            }
+            for (int i = 0; i < B200_FM_OPT; ++i) e[i] = fmaf(taps->apow[i], cin, e[i]);
+            float4 *dst = reinterpret_cast<float4 *>(s_e + B200_FM_HPAD + tid * B200_FM_OPT);
+            dst[0] = make_float4(e[0], e[1], e[2], e[3]);
+            dst[1] = make_float4(e[4], e[5], e[6], e[7]);
+            dst[2] = make_float4(e[8], e[9], e[10], e[11]);
         }
         __syncthreads(); /* S4 */
 
-        /* ---- stage 2: audio[p] = sum_k h2[k] e[5 p - k] for 5 p in this tile ---- */
+        /* ---- stage 2: audio[p] = sum_k h2[k] e[5 p - k]; a thread takes 3 consecutive p and reads
+         * its 60-sample window of e[] once ---- */
         {
-            const uint64_t mg0 = p.m_base + m0;                   /* global stage-1 index of tile start */
-            const uint64_t pg_first = (mg0 + B200_FM_D2 - 1) / B200_FM_D2; /* first global audio index */
-            for (uint64_t pg = pg_first + (uint64_t)tid;; pg += B200_FM_THREADS) {
-                const uint64_t mg = pg * B200_FM_D2;
-                if (mg >= mg0 + B200_FM_TILE_OUT || mg - p.m_base >= p.m1) break;
-                const float *win = s_e + B200_FM_HIST + (int)(mg - mg0);
-                float s = 0.0f;
+            const uint64_t mg0 = p.m_base + m0; /* global stage-1 index of tile start */
+            uint64_t mg_end = mg0 + (uint64_t)(last + 1) * B200_FM_OPT;
+            if (mg_end > p.m_base + p.m1) mg_end = p.m_base + p.m1;
+            const uint64_t pg_first = (mg0 + B200_FM_D2 - 1) / B200_FM_D2;
+            const uint64_t pg_end = (mg_end + B200_FM_D2 - 1) / B200_FM_D2;
+            const uint64_t pg0 = pg_first + (uint64_t)tid * B200_FM_APT;
+            if (pg0 < pg_end) {
+                const float *win = s_e + B200_FM_HPAD + (int)(pg0 * B200_FM_D2 - mg0) - B200_FM_HIST;
+                float ew[B200_FM_T2 + B200_FM_D2 * (B200_FM_APT - 1)];
 #pragma unroll
-                for (int k = 0; k < B200_FM_T2; ++k) s = fmaf(taps->h2[k], win[-k], s);
-                if (store) {
-                    const uint64_t pl = pg - p.audio_base; /* index into this launch's audio buffer */
-                    p.audio[(uint64_t)capture * p.audio_stride + pl] = s;
+                for (int j = 0; j < B200_FM_T2 + B200_FM_D2 * (B200_FM_APT - 1); ++j) ew[j] = win[j];
+#pragma unroll
+                for (int r = 0; r < B200_FM_APT; ++r) {
+                    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < B200_FM_T2; k += 2) {
+                        s0 = fmaf(taps->h2[k], ew[B200_FM_HIST + B200_FM_D2 * r - k], s0);
+                        s1 = fmaf(taps->h2[k + 1], ew[B200_FM_HIST + B200_FM_D2 * r - k - 1], s1);
+                    }
+                    if (store && pg0 + r < pg_end)
+                        p.audio[(uint64_t)capture * p.audio_stride + (pg0 + r - p.audio_base)] = s0 + s1;
                 }
             }
         }
         __syncthreads(); /* S5 */
         /* e carries for the next tile (tails / ylast travel through the parity buffers) */
-        if (tid == 9) s_wsum[4] = s_e[B200_FM_HIST + (last + 1) * B200_FM_OPT - 1];
-        if (tid >= 32 && tid < 32 + B200_FM_HIST) s_e[tid - 32] = s_e[(last + 1) * B200_FM_OPT + tid - 32];
+        if (tid == 9) s_wsum[4] = s_e[B200_FM_HPAD + (last + 1) * B200_FM_OPT - 1];
+        float hv = 0.0f;
+        if (tid >= 32 && tid < 32 + B200_FM_HIST) hv = s_e[B200_FM_HPAD + (last + 1) * B200_FM_OPT - B200_FM_HIST + tid - 32];
+        __syncthreads(); /* S6: history source read before it is overwritten (partial tiles overlap) */
+        if (tid >= 32 && tid < 32 + B200_FM_HIST) s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32] = hv;
         /* the next tile's S1..S3 order these writes before their readers */
     }
 
@@ -345,7 +387,8 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 2) k_wbfm(FmParams p)
             p.state[capture].ylast[1] = yi;
         }
         if (tid == 9) p.state[capture].e_last = s_wsum[4];
-        if (tid >= 32 && tid < 32 + B200_FM_HIST) p.state[capture].e_hist[tid - 32] = s_e[tid - 32];
+        if (tid >= 32 && tid < 32 + B200_FM_HIST)
+            p.state[capture].e_hist[tid - 32] = s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32];
     }
 }
 

@@ -77,6 +77,16 @@ def spec_check(out, gold, rtol=SPEC_RTOL):
     assert rel.max() <= rtol, f"max rel err {rel.max():.3e} at bin {rel.argmax()}"
 
 
+def spec_check_few_frames(out, gold):
+    """With only a handful of frames nothing averages the fp32 rounding noise of the strongest
+    component down, so a weak bin next to a strong tone cannot meet 1e-5 of ITS OWN power: the
+    achievable bound is eps * sqrt(P_k * P_max).  (The BASELINE configs average 255 / 46 874
+    frames and are held to the plain 1e-5.)"""
+    err = np.abs(out.astype(np.float64) - gold)
+    bound = 1e-5 * gold + 4e-7 * np.sqrt(gold * gold.max())
+    assert np.all(err <= bound), f"worst excess {np.max(err / bound):.2f}x at bin {np.argmax(err / bound)}"
+
+
 def test_spectrum_config0_block(sdr, g):
     """BASELINE config[0]: one 256 KiB block -> 1024-pt Hann FFT power spectrum (255 frames)."""
     iq = g.synth(1, 262144, SYNTH_MULTITONE, 0)
@@ -88,7 +98,7 @@ def test_spectrum_config0_block(sdr, g):
 
 def test_spectrum_golden_fixture(sdr, sdr_lib, vec):
     iq = sdr_lib.synth_fill_host(1, int(vec["spec_len"]), SYNTH_MULTITONE, int(vec["spec_seed"]))
-    spec_check(sdr.spectrum(iq)[0], vec["spec_hann_mean"], rtol=3e-5)  # only 15 frames averaged
+    spec_check_few_frames(sdr.spectrum(iq)[0], vec["spec_hann_mean"])  # only 15 frames averaged
 
 
 @pytest.mark.parametrize("n_captures,len_each", [(1, 2048), (3, 2048 + 1024 * 7 + 16), (5, 262144), (2, 4 * 262144)])
@@ -97,7 +107,7 @@ def test_spectrum_batches(sdr, g, n_captures, len_each):
     out = sdr.spectrum(iq, n_captures)
     for c in range(n_captures):
         gold, frames = g.spectrum(iq[c * len_each:(c + 1) * len_each])
-        spec_check(out[c], gold, rtol=SPEC_RTOL if frames >= 200 else 5e-5)
+        spec_check(out[c], gold) if frames >= 200 else spec_check_few_frames(out[c], gold)
 
 
 def test_spectrum_short_capture_is_zero(sdr):
@@ -129,7 +139,7 @@ def test_spectrum_ema(sdr_lib, g):
     iq = g.synth(1, 262144, SYNTH_MULTITONE, 4)
     with sdr_lib.B200Sdr(avg_mode=AVG_EMA, ema_beta=0.1) as s:
         out = s.spectrum(iq)[0]
-    spec_check(out, g.spectrum(iq, avg_mode=AVG_EMA, beta=0.1)[0], rtol=5e-5)  # ~20 effective frames
+    spec_check_few_frames(out, g.spectrum(iq, avg_mode=AVG_EMA, beta=0.1)[0])  # ~20 effective frames
 
 
 def test_spectrum_parseval(sdr, g):
@@ -250,7 +260,7 @@ def test_streaming_ema_spectrum(sdr_lib, g):
     with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM, avg_mode=AVG_EMA, ema_beta=0.1) as s:
         feed(s, iq, random_cuts(iq.size, 32768, 3))
         spec, _ = s.get_spectrum()
-    spec_check(spec, g.spectrum(iq, avg_mode=AVG_EMA, beta=0.1)[0], rtol=5e-5)
+    spec_check_few_frames(spec, g.spectrum(iq, avg_mode=AVG_EMA, beta=0.1)[0])
 
 
 # -------------------------------------------------------------------------------------- ingest

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(512) k(float *out, long long *cyc, float seed)
     float x = seed + threadIdx.x * 1e-9f, y = 0.999f;
     u64 px = pk(x, x + 1e-9f), py = pk(y, y);
     uint32_t w = threadIdx.x * 2654435761u, acc32 = 0;
+    uint32_t iv[8];
+    for (int i = 0; i < 8; ++i) iv[i] = w + i;
     __shared__ u64 sm[1024];
     sm[threadIdx.x] = px; sm[threadIdx.x + 512] = py;
     for (int i = 0; i < 8; ++i) { a[i] = i * 0.1f; p[i] = pk(i * 0.1f, i * 0.2f); }
@@ -70,15 +72,61 @@ __global__ void __launch_bounds__(512) k(float *out, long long *cyc, float seed)
         } else if (MODE == 10) { // LDS.64 only
 #pragma unroll
             for (int i = 0; i < 8; ++i) { u64 v = *((volatile u64 *)&sm[(threadIdx.x + i * 32 + it) & 1023]); p[i] ^= v; }
-        } else if (MODE == 11) { // MUFU.RCP
+        } else if (MODE == 11) { // MUFU.RCP (loop-carried through an FADD so it cannot be folded)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+            for (int i = 0; i < 8; ++i) { float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[i])); a[i] = r + 1.0f; }
+        } else if (MODE == 12) { // IADD3 x8 independent chains
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+        } else if (MODE == 13) { // FFMA2 + IADD 1:1, all independent
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+            }
+        } else if (MODE == 14) { // FFMA + IADD 1:1
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(a[i]) : "f"(x), "f"(y));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+            }
+        } else if (MODE == 15) { // 2 FFMA2 + 1 IADD
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                if (i & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+            }
+        } else if (MODE == 16) { // 2 FFMA + 1 IADD
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(a[i]) : "f"(x), "f"(y));
+                if (i & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+            }
+        } else if (MODE == 17) { // FFMA2 with scalar .F32 multiplier from a register (FIR form)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("{ .reg .b64 t; mov.b64 t, {%2, %2}; fma.rn.f32x2 %0, %1, t, %0; }" : "+l"(p[i]) : "l"(px), "f"(a[i & 3]));
+        } else if (MODE == 18) { // PRMT x8 independent
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("prmt.b32 %0, %0, %1, 0x7504;" : "+r"(iv[i]) : "r"(w));
+        } else if (MODE == 19) { // FFMA2 + PRMT 1:1 independent
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                asm volatile("prmt.b32 %0, %0, %1, 0x7504;" : "+r"(iv[i]) : "r"(w));
+            }
+        } else if (MODE == 20) { // FFMA2 + LDS.32 conflict-free 2:1
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                if (i & 1) { uint32_t v = *((volatile uint32_t *)&sm[0] + ((threadIdx.x + i * 32 + it) & 2047)); iv[i] ^= v; }
+            }
         }
     }
     long long t1 = clock64();
     float s = 0; u64 q = 0;
     for (int i = 0; i < 8; ++i) { s += a[i]; q ^= p[i]; }
-    if (s == 1234.5f || q == 77 || acc32 == 99) out[0] = s;
+    uint32_t z = 0; for (int i = 0; i < 8; ++i) z ^= iv[i];
+    if (s == 1234.5f || q == 77 || acc32 == 99 || z == 12345) out[0] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
@@ -116,6 +164,15 @@ int main()
     run<5>("I2F.U8 (+FADD)", 8, 0);
     run<10>("LDS.64", 8, 0);
     run<6>("FFMA2 + LDS.64 1:1", 16, 1);
-    run<11>("MUFU.RCP", 8, 0);
+    run<11>("MUFU.RCP (+FADD)", 16, 0);
+    run<12>("IADD x8 indep", 8, 0);
+    run<18>("PRMT x8 indep", 8, 0);
+    run<13>("FFMA2 + IADD 1:1 indep", 16, 1);
+    run<19>("FFMA2 + PRMT 1:1 indep", 16, 1);
+    run<14>("FFMA + IADD 1:1 indep", 16, 0.5);
+    run<15>("FFMA2 + IADD 2:1", 12, 4.0 / 3);
+    run<16>("FFMA + IADD 2:1", 12, 2.0 / 3);
+    run<17>("FFMA2 scalar-bcast multiplier", 8, 2);
+    run<20>("FFMA2 + LDS.32 2:1", 12, 4.0 / 3);
     return 0;
 }
