@@ -9,8 +9,8 @@
  * oracle/golden.c gold_wbfm().
  *
  * Work split.  grid = (segments, captures).  A CTA of 128 threads walks the tiles of its segment
- * in order; a tile is 128 x 120 input samples (30 720 bytes) brought in by one TMA bulk copy,
- * double buffered.
+ * in order; a tile is 128 x 120 input samples (30 720 bytes) brought in by one TMA bulk copy into a
+ * single buffer that is re-armed as soon as the FIR has consumed it (4 CTAs per SM overlap the rest).
  *
  * Stage 1 is written "input-partitioned": thread t owns input samples [a, a+120), a = tile + 120 t,
  * converts each byte pair exactly once (PRMT + one packed FADD) and scatters it into the (at most
