@@ -136,6 +136,25 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node the GPU hangs off, so
+    the host->device copies of several ranks do not cross the socket interconnect."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1B:00.0 -> 0000:1b:00.0
+        cpus = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+    except Exception:
+        pass
+
+
 # ---------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -161,6 +180,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -197,11 +217,16 @@ def main():
             sdr.synth_fill_dev(iq.data_ptr() + c * CAPTURE_BYTES, 1, CAPTURE_BYTES, kind, first_capture=lo + c)
     sdr.sync()
 
+    n_am = pkg.am_audio_len(CAPTURE_BYTES)
+    am_audio = torch.empty(B * n_am, dtype=torch.float32, device="cuda")
+
     def step(which=3):
         if which & 1:
             sdr.batch_spectrum_dev(iq.data_ptr(), B, CAPTURE_BYTES, spec.data_ptr())
         if which & 2:
             sdr.batch_wbfm_dev(iq.data_ptr(), B, CAPTURE_BYTES, audio.data_ptr())
+        if which & 4:   # secondary chain (config[3]); not part of the headline step
+            sdr.batch_am_dev(iq.data_ptr(), B, CAPTURE_BYTES, am_audio.data_ptr())
 
     def timed(which, steps):
         barrier()
@@ -223,6 +248,9 @@ def main():
     ms_spec = timed(1, args.steps)
     ms_fm = timed(2, args.steps)
     clocks = sampler.stop()
+    step(4)
+    sdr.sync()
+    ms_am = timed(4, args.steps)
 
     samples_step = B * CAPTURE_SAMPLES * world              # whole job, per step
     value = samples_step * args.steps / (ms_total * 1e-3) / 1e6
@@ -230,6 +258,8 @@ def main():
     spec_gbs = 2.0 * B * CAPTURE_SAMPLES * args.steps / (ms_spec * 1e-3) / 1e9            # per GPU
     fm_bytes = 2.0 + 4.0 * 48000.0 / 2400000.0
     fm_gbs = fm_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_fm * 1e-3) / 1e9
+    am_bytes = 2.0 + 4.0 * 8000.0 / 2400000.0
+    am_gbs = am_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer entry point --------------------------------------
     E = min(args.e2e_captures, B)
@@ -279,6 +309,9 @@ def main():
                              "GBps": spec_gbs, "hbm_frac": spec_gbs / hbm_peak},
                 "wbfm": {"ms_per_step": ms_fm / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_fm * 1e-3) / 1e6,
                          "GBps": fm_gbs, "hbm_frac": fm_gbs / hbm_peak, "algorithmic_bytes_per_sample": fm_bytes},
+                "am": {"ms_per_step": ms_am / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e6,
+                       "GBps": am_gbs, "hbm_frac": am_gbs / hbm_peak, "algorithmic_bytes_per_sample": am_bytes,
+                       "note": "config[3], secondary; not part of `value`"},
             },
             "cpu_baseline": cpu,
         }

@@ -8,6 +8,7 @@
  *   USBH/Src/usbh_ioreq.c            USBH_BulkReceiveData (:218-232)
  *   HAL_Driver/Src/stm32f7xx_hal_hcd.c   HAL_HCD_HC_SubmitRequest (:331-448), HAL_HCD_IRQHandler (:455-551),
  *                                        HCD_HC_IN_IRQHandler (:801-937), HCD_RXQLVL_IRQHandler (:1087-1132)
+ *   RTL/Src/tuner_e4k.c              E4K_compute_pll_params (:689-737), for the front-end KATs
  *   HAL_Driver/Src/stm32f7xx_ll_usb.c    USB_HC_Init, USB_HC_StartXfer (:1426-1530), USB_ReadPacket (:792-803),
  *                                        USB_HC_Halt -- through ll_usb_shim.c (FIFO register redirected)
  *
@@ -34,6 +35,7 @@
 #include "stm32f7xx_hal.h"
 #include "usbh_core.h"
 #include "usbh_rtlsdr.h"
+#include "tuner_e4k.h"
 
 /* ---- from ll_usb_shim.c ---- */
 void ref_fifo_set_source(const uint8_t *src);
@@ -58,7 +60,7 @@ uint32_t ref_read_packet(uint8_t *dest, const uint8_t *src, uint16_t len)
  * 2. stubs and glue
  * ------------------------------------------------------------------------------------------- */
 uint32_t SystemCoreClock = 200000000u; /* src/main.c:240-258: 200 MHz */
-RTLSDR_TunerTypeDef Tuner_E4K;         /* never touched by the sample path */
+/* Tuner_E4K comes from the reference's own tuner_e4k.c (linked for the PLL-parameter KATs) */
 
 static HCD_HandleTypeDef g_hhcd;
 static USBH_HandleTypeDef g_host;
@@ -272,11 +274,75 @@ long ref_run_stream(const uint8_t *stream, size_t total, uint32_t buff_size, uin
     return (long)blocks;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * 4. front-end parameter math of the reference (section 8f rows 2 and 4), called as the firmware
+ * calls it: the first state of each routine does the arithmetic and stores it in the handle.
+ * ------------------------------------------------------------------------------------------- */
+int ref_set_sample_rate(uint32_t rate, uint32_t *rsamp_ratio, uint32_t *real_rsamp_ratio, double *real_rate)
+{
+    if (ref_class_init() != 0) return -1;
+    handle()->setSampleRateState = 0;
+    RTLSDR_set_sample_rate(&g_host, rate); /* usbh_rtlsdr.c:666-700, state 0 */
+    *rsamp_ratio = handle()->rsamp_ratio;
+    *real_rsamp_ratio = handle()->real_rsamp_ratio;
+    *real_rate = handle()->real_rate;
+    return 0;
+}
+
+int ref_fir_bytes(uint8_t out20[20])
+{
+    if (ref_class_init() != 0) return -1;
+    handle()->firState = RTLSDR_FIR_CALC;
+    RTLSDR_set_fir(&g_host); /* usbh_rtlsdr.c:534-575, state RTLSDR_FIR_CALC */
+    memcpy(out20, handle()->fir, 20);
+    return 0;
+}
+
+/* out8: fosc, intended_flo, flo, x, z, r, r_idx, threephase */
+uint32_t ref_e4k_pll(uint32_t fosc, uint32_t intended_flo, uint32_t out8[8])
+{
+    struct e4k_pll_params p;
+    memset(&p, 0, sizeof p);
+    uint32_t flo = E4K_compute_pll_params(&p, fosc, intended_flo); /* tuner_e4k.c:689-737 */
+    out8[0] = p.fosc; out8[1] = p.intended_flo; out8[2] = p.flo; out8[3] = p.x;
+    out8[4] = p.z; out8[5] = p.r; out8[6] = p.r_idx; out8[7] = p.threephase;
+    return flo;
+}
+
 #ifdef REF_CLI
+static int cli_frontend(int argc, char **argv)
+{
+    if (strcmp(argv[1], "--rate") == 0 && argc >= 3) {
+        uint32_t a, b; double r;
+        if (ref_set_sample_rate((uint32_t)strtoul(argv[2], 0, 0), &a, &b, &r)) return 1;
+        printf("REF_RATE %u %u %.17g\n", a, b, r);
+        return 0;
+    }
+    if (strcmp(argv[1], "--fir") == 0) {
+        uint8_t f[20];
+        if (ref_fir_bytes(f)) return 1;
+        printf("REF_FIR ");
+        for (int i = 0; i < 20; ++i) printf("%02x", f[i]);
+        printf("\n");
+        return 0;
+    }
+    if (strcmp(argv[1], "--e4k") == 0 && argc >= 4) {
+        uint32_t o[8];
+        uint32_t flo = ref_e4k_pll((uint32_t)strtoul(argv[2], 0, 0), (uint32_t)strtoul(argv[3], 0, 0), o);
+        printf("REF_E4K %u %u %u %u %u %u %u %u %u\n", flo, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+        return 0;
+    }
+    return -1;
+}
+
 /* ref_ingest_cli <in.bin> <buff_size> <tim_cnt> <out.bin>
  * stdout: the reference's own log lines, then one summary line starting with "REF_SUMMARY". */
 int main(int argc, char **argv)
 {
+    if (argc >= 2 && argv[1][0] == '-') {
+        int rc = cli_frontend(argc, argv);
+        if (rc >= 0) return rc;
+    }
     if (argc < 5) { fprintf(stderr, "usage: %s in.bin buff_size tim_cnt out.bin\n", argv[0]); return 2; }
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 3;

@@ -47,7 +47,8 @@ _lib = None
 
 def declared_symbols():
     """Every function include/b200sdr.h declares with B200SDR_API (for the export check)."""
-    text = open(HEADER_PATH).read()
+    inc = os.path.dirname(HEADER_PATH)
+    text = open(HEADER_PATH).read() + open(os.path.join(inc, "b200sdr_frontend.h")).read()
     return sorted(set(re.findall(r"B200SDR_API\s+[\w\s\*]+?\b(\w+)\s*\(", text)))
 
 
@@ -131,6 +132,49 @@ def synth_fill_host(n_captures, len_each, kind, first_capture=0):
     if rc != OK:
         raise B200SdrError(rc, "b200sdr_synth_fill_host")
     return buf
+
+
+class RtlRate(C.Structure):
+    _fields_ = [("rsamp_ratio", C.c_uint32), ("real_rsamp_ratio", C.c_uint32), ("real_rate", C.c_double)]
+
+
+class E4kPll(C.Structure):
+    _fields_ = [("fosc", C.c_uint32), ("intended_flo", C.c_uint32), ("flo", C.c_uint32), ("x", C.c_uint16),
+                ("z", C.c_uint8), ("r", C.c_uint8), ("r_idx", C.c_uint8), ("threephase", C.c_uint8)]
+
+
+def rtl_resampler(samp_rate, xtal_hz=28800000):
+    """include/b200sdr_frontend.h: (status, rsamp_ratio, real_rsamp_ratio, real_rate)."""
+    lib = load_library()
+    lib.b200sdr_rtl_resampler.restype = C.c_int32
+    lib.b200sdr_rtl_resampler.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(RtlRate)]
+    out = RtlRate()
+    rc = lib.b200sdr_rtl_resampler(samp_rate, xtal_hz, C.byref(out))
+    return rc, out.rsamp_ratio, out.real_rsamp_ratio, out.real_rate
+
+
+def rtl_fir_pack(coeff=None):
+    lib = load_library()
+    lib.b200sdr_rtl_default_fir.argtypes = [C.POINTER(C.c_int32)]
+    lib.b200sdr_rtl_fir_pack.restype = C.c_int32
+    lib.b200sdr_rtl_fir_pack.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]
+    c = (C.c_int32 * 16)()
+    if coeff is None:
+        lib.b200sdr_rtl_default_fir(c)
+    else:
+        c[:] = list(coeff)
+    out = (C.c_uint8 * 20)()
+    rc = lib.b200sdr_rtl_fir_pack(c, out)
+    return rc, bytes(out), list(c)
+
+
+def e4k_pll_params(fosc, intended_flo):
+    lib = load_library()
+    lib.b200sdr_e4k_pll_params.restype = C.c_uint32
+    lib.b200sdr_e4k_pll_params.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(E4kPll)]
+    p = E4kPll()
+    flo = lib.b200sdr_e4k_pll_params(fosc, intended_flo, C.byref(p))
+    return flo, (p.fosc, p.intended_flo, p.flo, p.x, p.z, p.r, p.r_idx, p.threephase)
 
 
 def _u8(a):

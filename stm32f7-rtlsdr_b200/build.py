@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sdr.so")
-SOURCES = [os.path.join(CSRC, "api.cu")]
+SOURCES = [os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "frontend.cpp")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source_mtime():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + SOURCES
+    extra = os.environ.get("B200_NVCC_EXTRA", "").split()  # experiment knobs, e.g. -DB200_SPEC_MINB=4
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", OUT] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:

@@ -33,6 +33,12 @@
 
 #include "fft32.cuh"
 
+#ifndef B200_SPEC_MINB
+#define B200_SPEC_MINB 3 /* CTAs per SM the register allocation is tuned for */
+#endif
+#ifndef B200_SPEC_PREFETCH
+#define B200_SPEC_PREFETCH 1 /* issue the loads of frame m+1 before the FFT of frame m */
+#endif
 #define B200_SPEC_WARPS 4
 #define B200_SPEC_THREADS (32 * B200_SPEC_WARPS)
 #define B200_SPEC_XP 33 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free */
@@ -64,7 +70,7 @@ struct SpectrumParams {
 };
 
 template <bool EMA>
-__global__ void __launch_bounds__(B200_SPEC_THREADS, 3) k_spectrum(SpectrumParams p)
+__global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(SpectrumParams p)
 {
     B200_DYN_SMEM(smem);
     float *s_win = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_WIN);
@@ -98,12 +104,16 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, 3) k_spectrum(SpectrumParam
      * so no warp ever waits on HBM/L2 latency with only three warps per scheduler resident */
     const unsigned short *src0 = reinterpret_cast<const unsigned short *>(cap) + (uint32_t)lane;
     uint32_t raw[32];
-    if (m_begin < m_end) {
+    if (B200_SPEC_PREFETCH && m_begin < m_end) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m_begin * 512u + 32 * j);
     }
     for (uint32_t m = m_begin; m < m_end; ++m) {
         c2 v[32];
+        if (!B200_SPEC_PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m * 512u + 32 * j);
+        }
         /* convert + window, written to the bit-reversed slot pass 1 wants */
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, 3) k_spectrum(SpectrumParam
                 v[b200_bitrev5(j)] = c2_scale(c2_from_u8_lo(raw[j]), wj[jj]);
             }
         }
-        if (m + 1 < m_end) {
+        if (B200_SPEC_PREFETCH && m + 1 < m_end) {
             const unsigned short *src = src0 + (uint64_t)(m + 1) * 512u;
 #pragma unroll
             for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src + 32 * j);

@@ -1,0 +1,88 @@
+"""the RTL2832 / E4000 front-end parameter math of the product
+(include/b200sdr_frontend.h, host-only) against the reference's OWN routines compiled on the host
+(oracle A: RTLSDR_set_sample_rate, RTLSDR_set_fir, E4K_compute_pll_params) -- bit-exact -- plus
+the KATs of SURVEY section 4 that need no reference build.  CPU only."""
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "oracle", "_ref", "ref_ingest_cli")
+have_ref = os.path.exists(CLI)
+
+
+@pytest.fixture(scope="module")
+def b(sdr_lib):
+    return importlib.import_module("stm32f7-rtlsdr_b200.binding")
+
+
+def ref(*args):
+    out = subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, check=True).stdout
+    return [l for l in out.splitlines() if l.startswith("REF_")][-1].split()[1:]
+
+
+def test_kats_from_the_survey(b):
+    # 240 kS/s (the rate the firmware programs, usbh_rtlsdr.c:898), 2.4 MS/s, 2.048 MS/s
+    assert b.rtl_resampler(240000)[1:] == (0x0E000000, 0x1E000000, 240000.0)
+    assert b.rtl_resampler(2400000) == (0, 0x03000000, 0x03000000, 2400000.0)
+    assert b.rtl_resampler(2048000)[1] == 0x03840000
+    rc, packed, coeff = b.rtl_fir_pack()
+    assert rc == 0 and packed.hex() == "cadcd7d8e0f20e3506509c0d71111471741941a5"
+    assert coeff[:3] == [-54, -36, -41] and coeff[-1] == 421
+
+
+def test_unsupported_rates_are_reported(b):
+    for rate in (225000, 300001, 900000, 3200001):
+        assert b.rtl_resampler(rate)[0] == 3  # B200SDR_NOT_SUPPORTED
+    for rate in (225001, 300000, 900001, 3200000):
+        assert b.rtl_resampler(rate)[0] == 0
+
+
+def test_fir_pack_range_check(b):
+    c = [0] * 16
+    c[3] = 128
+    assert b.rtl_fir_pack(c)[0] == 3
+    c[3] = 0
+    c[9] = -2049
+    assert b.rtl_fir_pack(c)[0] == 3
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+def test_resampler_bit_exact_against_reference(b):
+    rates = [240000, 250000, 288000, 300000, 900001, 960000, 1024000, 1200000, 1400000, 1536000, 1800000, 1920000,
+             2048000, 2400000, 2560000, 2880000, 3200000, 225001, 1000001, 2399999]
+    rates += [int(x) for x in np.random.default_rng(0).integers(226000, 3200000, 40)]
+    for rate in rates:
+        a, r, real = ref("--rate", rate)
+        _, ratio, applied, real_rate = b.rtl_resampler(rate)
+        assert (ratio, applied) == (int(a), int(r)), rate
+        assert real_rate == float(real), rate  # %.17g round-trips a double exactly
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+def test_fir_bytes_bit_exact_against_reference(b):
+    assert b.rtl_fir_pack()[1].hex() == ref("--fir")[0]
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+def test_e4k_pll_bit_exact_against_reference(b):
+    fosc = 28800000
+    freqs = [99700000,                       # the frequency the firmware tunes (tuner_e4k.c:1084)
+             52000000, 72399999, 72400000, 81200000, 108300000, 162500000, 216600000, 325000000, 350000000,
+             432000000, 667000000, 1199999999, 1200000000, 1700000000, 2200000000]
+    freqs += [int(x) for x in np.random.default_rng(1).integers(50_000_000, 2_200_000_000, 60)]
+    for f in freqs:
+        for osc in (fosc, 16000000, 30000000, 26000000):
+            want = [int(v) for v in ref("--e4k", osc, f)]
+            flo, fields = b.e4k_pll_params(osc, f)
+            assert [flo, *fields] == want, (osc, f)
+    # invalid oscillator -> 0, like is_fosc_valid()
+    assert b.e4k_pll_params(15999999, 100000000)[0] == int(ref("--e4k", 15999999, 100000000)[0]) == 0
+
+
+def test_e4k_kat_at_the_firmware_frequency(b):
+    flo, (fosc, want, got, x, z, r, r_idx, three) = b.e4k_pll_params(28800000, 99700000)
+    assert (flo, got, x, z, r, r_idx, three) == (99699993, 99699993, 50972, 110, 32, 13, 1)
