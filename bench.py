@@ -139,6 +139,8 @@ def run_reference(args, rank, world):
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank (and first-touch its pinned buffers) on the NUMA node the GPU hangs off, so
     the host->device copies of several ranks do not cross the socket interconnect."""
+    if os.environ.get("B200_BENCH_NUMA", "0") != "1":
+        return
     try:
         out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
                              capture_output=True, text=True, timeout=20).stdout.strip().lower()
@@ -163,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--captures-per-gpu", type=int, default=512)
-    ap.add_argument("--e2e-captures", type=int, default=32)
+    ap.add_argument("--e2e-captures", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

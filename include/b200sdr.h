@@ -180,6 +180,18 @@ B200SDR_API int32_t b200sdr_convert_cf32(b200sdr_ctx *ctx, const uint8_t *iq_hos
 B200SDR_API int32_t b200sdr_convert_cf32_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64_t len, uint32_t window,
                                              float *out_dev);
 
+/* ------------------------------------------------------------------------------------------
+ * Presentation: a power spectrum as a 480 x 272 ARGB8888 bar plot --
+ * the geometry and pixel format of the LCD layer the firmware's sample buffer aliases
+ * (src/main.c:100-109).  Column 0 is -fs/2, the centre column is DC; dB = 10 log10(power) mapped
+ * from [db_min, db_max] to the 272 rows.  spectrum_host == NULL renders the current streaming
+ * spectrum.  `_dev` renders n spectra resident on the device (values are multiplied by `scale`).
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t b200sdr_render_spectrum(b200sdr_ctx *ctx, const float *spectrum_host, float db_min, float db_max,
+                                            uint32_t *argb_host /* 480*272 */);
+B200SDR_API int32_t b200sdr_render_spectrum_dev(b200sdr_ctx *ctx, const float *spectra_dev, uint32_t n_spectra,
+                                                float scale, float db_min, float db_max, uint32_t *argb_dev);
+
 /* The FIR taps / window the device uses (float, as uploaded), for parity against the oracle. */
 B200SDR_API int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *out, uint32_t capacity,
                                      uint32_t *n_taps);

@@ -380,6 +380,44 @@ void gold_am(const uint8_t *iq, size_t n, real *audio)
     free(y1); free(y2); free(b);
 }
 
+/* ---- presentation: 480 x 272 ARGB8888 bar plot of a power spectrum (section 8f row 3) -------
+ * No counterpart in the reference beyond the LCD layer geometry / pixel format
+ * (src/main.c:100-109, stm32746g_discovery_lcd.h:123-134).  `power` is float32 on purpose: the
+ * image is defined on the values the device produced, so the comparison is bit-exact. */
+void gold_render_thresholds(double db_min, double db_max, float *thr272)
+{
+    for (int h = 0; h < 272; ++h) thr272[h] = (float)pow(10.0, (db_min + (db_max - db_min) * (double)h / 271.0) / 10.0);
+}
+
+void gold_render_spectrum(const float *power1024, double db_min, double db_max, uint32_t *argb)
+{
+    float thr[272];
+    gold_render_thresholds(db_min, db_max, thr);
+    for (int c = 0; c < 480; ++c) {
+        int s0 = (c * 1024) / 480, s1 = ((c + 1) * 1024) / 480;
+        float v = 0.0f;
+        for (int s = s0; s < s1; ++s) {
+            float pw = power1024[(s + 512) & 1023];
+            if (pw > v) v = pw;
+        }
+        int height = 0;
+        while (height < 272 && thr[height] <= v) height++;
+        for (int r = 0; r < 272; ++r) {
+            int y = 271 - r;
+            uint32_t px = 0xFF000000u;
+            if (y < height) {
+                int i = (y * 255) / 271, seg = i / 64, t = (i % 64) * 4, rr, gg, bb;
+                if (seg == 0) { rr = 0; gg = t; bb = 255; }
+                else if (seg == 1) { rr = 0; gg = 255; bb = 255 - t; }
+                else if (seg == 2) { rr = t; gg = 255; bb = 0; }
+                else { rr = 255; gg = 255 - t; bb = 0; }
+                px |= ((uint32_t)rr << 16) | ((uint32_t)gg << 8) | (uint32_t)bb;
+            }
+            argb[r * 480 + c] = px;
+        }
+    }
+}
+
 /* ---- synthetic captures ------------------------------------------------------------------ */
 static float g_lut[B200SDR_SYNTH_LUT_SIZE + 1];
 static int g_lut_ready = 0;

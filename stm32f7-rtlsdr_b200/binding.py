@@ -370,6 +370,19 @@ class B200Sdr:
         self._check(self.lib.b200sdr_get_window(self.ctx, window, out.ctypes.data), "b200sdr_get_window")
         return out
 
+    def render_spectrum(self, spectrum=None, db_min=0.0, db_max=100.0):
+        """480 x 272 ARGB8888 bar plot; spectrum=None renders the current streaming spectrum."""
+        fn = self.lib.b200sdr_render_spectrum
+        fn.restype = C.c_int32
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        img = np.empty((272, 480), dtype=np.uint32)
+        src = None
+        if spectrum is not None:
+            spectrum = np.ascontiguousarray(spectrum, dtype=np.float32)
+            src = spectrum.ctypes.data
+        self._check(fn(self.ctx, src, db_min, db_max, img.ctypes.data), "b200sdr_render_spectrum")
+        return img
+
     def synth_fill_dev(self, iq_dev, n_captures, len_each, kind, first_capture=0):
         self._check(self.lib.b200sdr_synth_fill_dev(self.ctx, iq_dev, n_captures, len_each, kind, first_capture), "b200sdr_synth_fill_dev")
 

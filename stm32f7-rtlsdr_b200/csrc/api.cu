@@ -22,6 +22,7 @@
 #include "../../include/b200sdr.h"
 #include "misc_kernels.cuh"
 #include "plan.h"
+#include "render.cuh"
 
 namespace {
 
@@ -50,6 +51,7 @@ struct b200sdr_ctx {
     float *d_window[3] = {nullptr, nullptr, nullptr};
     float2 *d_twiddle = nullptr;
     float *d_lut = nullptr;
+    float *d_thresholds = nullptr;
     std::vector<float> h_taps[5];
     std::vector<float> h_window[3];
 
@@ -525,7 +527,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     void *dev_ptrs[] = {ctx->d_ring, ctx->d_spec_buf, ctx->d_bounce, ctx->d_spec_acc, ctx->d_fm_buf, ctx->d_am_buf,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
-                        ctx->d_lut, ctx->d_partials, ctx->d_env};
+                        ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds};
     for (void *p : dev_ptrs) if (p) cudaFree(p);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -816,6 +818,58 @@ int32_t b200sdr_get_window(b200sdr_ctx *ctx, uint32_t window, float *out1024)
     if (!ctx || !out1024 || window > 2) return B200SDR_NOT_SUPPORTED;
     DeviceGuard guard(ctx->device);
     CU(cudaMemcpy(out1024, ctx->d_window[window], 1024 * sizeof(float), cudaMemcpyDeviceToHost)); /* as the kernels see it */
+    return B200SDR_OK;
+}
+
+/* ---- presentation (section 8f row 3) ------------------------------------------------------- */
+int32_t b200sdr_render_spectrum_dev(b200sdr_ctx *ctx, const float *spectra_dev, uint32_t n_spectra, float scale,
+                                    float db_min, float db_max, uint32_t *argb_dev)
+{
+    if (!ctx || !spectra_dev || !argb_dev) return B200SDR_FAIL;
+    if (!(db_max > db_min)) return fail(ctx, B200SDR_NOT_SUPPORTED, "db_max must exceed db_min");
+    if (n_spectra == 0) return B200SDR_OK;
+    DeviceGuard guard(ctx->device);
+    float thr[B200_LCD_H];
+    for (int h = 0; h < B200_LCD_H; ++h)
+        thr[h] = (float)pow(10.0, ((double)db_min + ((double)db_max - (double)db_min) * (double)h / (B200_LCD_H - 1.0)) / 10.0);
+    if (!ctx->d_thresholds) CU(cudaMalloc((void **)&ctx->d_thresholds, sizeof thr));
+    CU(cudaMemcpyAsync(ctx->d_thresholds, thr, sizeof thr, cudaMemcpyHostToDevice, ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_compute)); /* `thr` is a stack buffer */
+    k_render_spectrum<<<n_spectra, B200_LCD_W, 0, ctx->s_compute>>>(spectra_dev, scale, ctx->d_thresholds, argb_dev);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_render_spectrum(b200sdr_ctx *ctx, const float *spectrum_host, float db_min, float db_max, uint32_t *argb_host)
+{
+    if (!ctx || !argb_host) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    const size_t img_bytes = (size_t)B200_LCD_W * B200_LCD_H * sizeof(uint32_t);
+    uint32_t *d_img = nullptr;
+    float *d_spec = nullptr;
+    CU(cudaMalloc((void **)&d_img, img_bytes));
+    int rc = B200SDR_OK;
+    cudaError_t e = cudaSuccess;
+    do {
+        const float *src = ctx->d_spec_acc;
+        float scale = 1.0f;
+        if (spectrum_host) {
+            if ((e = cudaMalloc((void **)&d_spec, 1024 * sizeof(float))) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_spec, spectrum_host, 1024 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_compute)) != cudaSuccess) break;
+            src = d_spec;
+        } else if (ctx->cfg.avg_mode == B200SDR_AVG_MEAN && ctx->spec_frames) {
+            scale = 1.0f / (float)ctx->spec_frames; /* the accumulator holds the sum */
+        }
+        rc = b200sdr_render_spectrum_dev(ctx, src, 1, scale, db_min, db_max, d_img);
+        if (rc) break;
+        if ((e = cudaMemcpyAsync(argb_host, d_img, img_bytes, cudaMemcpyDeviceToHost, ctx->s_compute)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(ctx->s_compute);
+    } while (0);
+    cudaFree(d_img);
+    if (d_spec) cudaFree(d_spec);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "render", e);
     return B200SDR_OK;
 }
 

@@ -1,0 +1,60 @@
+"""the 480 x 272 ARGB8888 spectrum image.  CPU: the golden definition
+itself; GPU: the device kernel through the C ABI, BIT-EXACT against the golden on the same float32
+power values."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle_api import SYNTH_MULTITONE, Golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def gold_render(g, power, db_min, db_max):
+    g.lib.gold_render_spectrum.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    p = np.ascontiguousarray(power, np.float32)
+    img = np.zeros((272, 480), np.uint32)
+    g.lib.gold_render_spectrum(p.ctypes.data, db_min, db_max, img.ctypes.data)
+    return img
+
+
+def test_golden_render_geometry_and_colours():
+    g = Golden()
+    power = np.full(1024, 1.0, np.float32)     # 0 dB everywhere
+    power[0] = 1e10                            # DC: 100 dB -> centre column, full height
+    power[512] = 1e5                           # -fs/2: 50 dB -> column 0, half height
+    img = gold_render(g, power, 0.0, 100.0)
+    assert img.shape == (272, 480) and img.dtype == np.uint32
+    assert np.all(img >> 24 == 0xFF)                                   # opaque ARGB8888
+    lit = (img & 0x00FFFFFF) != 0
+    assert lit[:, 240].all()                                           # DC column is full height
+    h0 = lit[:, 0].sum()
+    assert 135 <= h0 <= 137                                            # 50 dB of 100 dB over 272 rows
+    assert lit[:, 100].sum() == 1                                      # 0 dB == db_min: only T[0] <= 1.0
+    assert img[271, 240] == 0xFF0000FF and img[0, 240] == 0xFFFF0300   # blue at the bottom, red at the top
+    # bars are solid from the bottom
+    for c in (0, 100, 240):
+        col = lit[:, c]
+        assert not np.any(col[:-1] & ~col[1:])
+
+
+@pytest.mark.gpu
+def test_render_bit_exact_against_golden(sdr_lib):
+    g = Golden()
+    iq = g.synth(1, 262144, SYNTH_MULTITONE, 0)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        spec = s.spectrum(iq)[0]
+        for db_min, db_max in ((0.0, 100.0), (20.0, 90.0), (-10.0, 60.0)):
+            img = s.render_spectrum(spec, db_min, db_max)
+            assert np.array_equal(img, gold_render(g, spec, db_min, db_max))
+        # streaming accumulator (holds the sum; the kernel applies 1/frames like the host getter)
+        s.process_samples(iq)
+        spec2, frames = s.get_spectrum()
+        assert frames == 255
+        assert np.array_equal(s.render_spectrum(None, 0.0, 100.0), gold_render(g, spec2, 0.0, 100.0))
+        rnd = np.abs(np.random.default_rng(0).standard_normal(1024)).astype(np.float32) * 1e6
+        assert np.array_equal(s.render_spectrum(rnd, 10.0, 80.0), gold_render(g, rnd, 10.0, 80.0))
+        with pytest.raises(sdr_lib.B200SdrError):
+            s.render_spectrum(rnd, 50.0, 50.0)
