@@ -139,7 +139,11 @@ def run_reference(args, rank, world):
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank (and first-touch its pinned buffers) on the NUMA node the GPU hangs off, so
     the host->device copies of several ranks do not cross the socket interconnect."""
-    if os.environ.get("B200_BENCH_NUMA", "0") != "1":
+    try:
+        multi_node = "-" in open("/sys/devices/system/node/online").read() or "," in open("/sys/devices/system/node/online").read()
+    except OSError:
+        multi_node = False
+    if os.environ.get("B200_BENCH_NUMA", "1" if multi_node else "0") != "1":
         return
     try:
         out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
@@ -249,7 +253,6 @@ def main():
     launches = sdr.kernel_launches() - l0
     ms_spec = timed(1, args.steps)
     ms_fm = timed(2, args.steps)
-    clocks = sampler.stop()
     step(4)
     sdr.sync()
     ms_am = timed(4, args.steps)
@@ -279,9 +282,34 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = E * CAPTURE_SAMPLES * world * e2e_steps / e2e_s / 1e6
+    clocks = sampler.stop()   # sampled across all timed regions above (device-timed chains + e2e)
     checksum = float(h_spec[:1024].sum()) + float(h_fm[:1000].sum())
     for p in (hp, sp, fp):
         sdr.pinned_free(p)
+
+    # ---- streaming ingest through process_samples (ring -> H2D -> chains), labelled separately:
+    # launch- and PCIe-bound, what a live 2.4 MS/s dongle would exercise (needs 4.8 MB/s) ------
+    ingest = None
+    if rank == 0:
+        blk = 262144
+        s2 = pkg.B200Sdr(device=local_rank, chains=pkg.CHAIN_SPECTRUM | pkg.CHAIN_WBFM, slot_bytes=blk, ring_slots=8,
+                         audio_capacity=1 << 22)
+        src = pkg.synth_fill_host(1, blk * 16, pkg.SYNTH_WBFM, 0)
+        n_blocks, busy = 512, 0
+        for i in range(32):
+            s2.process_samples(src[(i % 16) * blk:(i % 16 + 1) * blk])
+        s2.sync()
+        s2.get_audio(pkg.CHAIN_WBFM, 1 << 22)
+        t0 = time.perf_counter()
+        for i in range(n_blocks):
+            view = src[(i % 16) * blk:(i % 16 + 1) * blk]
+            while s2.process_samples(view, allow_busy=True) == pkg.BUSY:
+                busy += 1  # every ring slot in flight: poll again (the audio FIFO holds the whole run)
+        s2.sync()
+        dt = time.perf_counter() - t0
+        ingest = {"api": "process_samples", "block_bytes": blk, "blocks": n_blocks, "MSps": n_blocks * blk / 2 / dt / 1e6,
+                  "us_per_block": dt / n_blocks * 1e6, "busy_returns": busy, "realtime_factor_at_2.4MSps": n_blocks * blk / 2 / dt / 2.4e6}
+        s2.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -303,7 +331,9 @@ def main():
                     "api": "b200sdr_batch_host (pinned host -> H2D -> kernels -> D2H)", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_spectrum (+k_spectrum_finalize)", "achieved": spec_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": spec_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": spec_gbs / hbm_peak,
+                         "traffic": 1.0074 * 2.0 * B * CAPTURE_SAMPLES,  # bytes per launch: ncu dram read+write = 1.0074 x algorithmic (profiles/r1_ncu_summary_v2.txt)
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": 2.0,
                          "note": "FP32-pipe bound, not HBM bound: ~2100 fp32 lane-ops per 512 new samples (DESIGN.md)"},
             "chains": {
@@ -315,6 +345,7 @@ def main():
                        "GBps": am_gbs, "hbm_frac": am_gbs / hbm_peak, "algorithmic_bytes_per_sample": am_bytes,
                        "note": "config[3], secondary; not part of `value`"},
             },
+            "ingest": ingest,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

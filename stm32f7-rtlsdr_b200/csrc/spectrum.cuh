@@ -39,6 +39,9 @@
 #ifndef B200_SPEC_PREFETCH
 #define B200_SPEC_PREFETCH 1 /* issue the loads of frame m+1 before the FFT of frame m */
 #endif
+#ifndef B200_SPEC_MERGE_TW
+#define B200_SPEC_MERGE_TW 1 /* fold the inter-pass twiddles into the first butterfly stage of pass 2 */
+#endif
 #define B200_SPEC_WARPS 4
 #define B200_SPEC_THREADS (32 * B200_SPEC_WARPS)
 #define B200_SPEC_XP 33 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free */
@@ -83,7 +86,13 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         int t = i & 31, j = i >> 5;
         s_win[t * B200_SPEC_WP + j] = __ldg(p.window + i);
         float2 w = __ldg(p.twiddle + ((t * j) & 1023));
+#if B200_SPEC_MERGE_TW
+        /* pair layout: [e][lane] = (W^{e lane}, W^{(e+16) lane}), e = 0..15: one 16-byte load feeds a
+         * first-stage butterfly of pass 2 (elements e and e+16 of lane's column) */
+        s_tw[((j & 15) * 32 + t) * 2 + (j >> 4)] = c2_make(w.x, w.y);
+#else
         s_tw[j * 32 + t] = c2_make(w.x, w.y);
+#endif
     }
     __syncthreads();
 
@@ -131,12 +140,14 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
             for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src + 32 * j);
         }
         b200_fft32(v); /* v[k1] = Y[k1] */
+#if !B200_SPEC_MERGE_TW
 #pragma unroll
         for (int k1 = 1; k1 < 32; ++k1) {
             float wr, wi;
             c2_get(s_tw[k1 * 32 + lane], wr, wi);
             v[k1] = c2_cmul(v[k1], wr, wi);
         }
+#endif
         /* transpose through the warp-private tile: row = k1 (the reader's lane), column = source lane t */
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) s_xp[k1 * B200_SPEC_XP + lane] = v[k1];
@@ -144,7 +155,26 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #pragma unroll
         for (int t = 0; t < 32; ++t) v[b200_bitrev5(t)] = s_xp[lane * B200_SPEC_XP + t];
         __syncwarp();
+#if B200_SPEC_MERGE_TW
+        /* first DIT stage of pass 2 with the four-step twiddles folded in: slots (2i, 2i+1) hold the
+         * elements e = bitrev5(2i) < 16 and e + 16 of this lane's column; X = Ta a + Tb b, Y = Ta a - Tb b
+         * = 2 (Ta a) - X: 5 packed ops instead of 2 + 2 (twiddles) + 2 (butterfly) */
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = b200_bitrev5(2 * i);
+            const float4 tw = *reinterpret_cast<const float4 *>(s_tw + (e * 32 + lane) * 2);
+            const c2 pa = (e == 0) ? v[2 * i] : c2_cmul(v[2 * i], tw.x, tw.y);
+            const c2 x = c2_cfma(v[2 * i + 1], tw.z, tw.w, pa);
+            v[2 * i + 1] = c2_two_a_minus(pa, x);
+            v[2 * i] = x;
+        }
+        b200_stage_k<4, 0>::run(v);
+        b200_stage_k<8, 0>::run(v);
+        b200_stage_k<16, 0>::run(v);
+        b200_stage_k<32, 0>::run(v); /* v[k2] = X[lane + 32 k2] */
+#else
         b200_fft32(v); /* v[k2] = X[lane + 32 k2] */
+#endif
         if (EMA) {
             float wgt = p.ema_beta * exp2f((float)(p.frames - 1u - m) * p.ema_log2_decay);
 #pragma unroll

@@ -153,13 +153,24 @@ static FmTaps c_fm_taps;
 __constant__ FmTaps c_fm_taps;
 #endif
 
+B200_DEV float b200_rcp_fast(float x)
+{
+#ifdef B200_PACKED
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 /* atan2(y, x), branch-free, ~1.3e-7 rad: one MUFU.RCP, a degree-15 odd minimax polynomial on
  * [0, 1] (fitted offline against float64 atan), then octant fix-ups.  atan2(0, 0) = 0. */
 B200_DEV float b200_atan2(float y, float x)
 {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
-    const float a = mn * __frcp_rn(mx);
+    const float a = mn * b200_rcp_fast(mx); /* MUFU.RCP, ~1 ulp; the IEEE-exact __frcp_rn costs a call */
     const float s = a * a;
     float p = -4.054550054e-03f;
     p = fmaf(p, s, 2.186289528e-02f);
@@ -299,9 +310,10 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
             if (p.disc && store) {
                 const uint64_t m = m0 + (uint64_t)tid * B200_FM_OPT;
                 float *dst = p.disc + (uint64_t)capture * p.disc_stride + m;
+                const int n_valid = p.m1 > m ? (p.m1 - m > B200_FM_OPT ? B200_FM_OPT : (int)(p.m1 - m)) : 0;
 #pragma unroll
                 for (int i = 0; i < B200_FM_OPT; ++i)
-                    if (m + i < p.m1) dst[i] = d[i];
+                    if (i < n_valid) dst[i] = d[i];
             }
             float run = 0.0f;
 #pragma unroll
