@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -243,16 +243,17 @@ def main():
         barrier()
         return max_over_ranks(ms)
 
+    sampler = ClockSampler(local_rank)   # polls nvidia-smi while the device-timed regions run (incl. warm-up:
+    sampler.start()                      # same load); stopped before e2e, whose PCIe copies the polling perturbs
     for _ in range(args.warmup):
         step()
     sdr.sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = sdr.kernel_launches()
     ms_total = timed(3, args.steps)
     launches = sdr.kernel_launches() - l0
     ms_spec = timed(1, args.steps)
     ms_fm = timed(2, args.steps)
+    clocks = sampler.stop()
     step(4)
     sdr.sync()
     ms_am = timed(4, args.steps)
@@ -282,7 +283,6 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = E * CAPTURE_SAMPLES * world * e2e_steps / e2e_s / 1e6
-    clocks = sampler.stop()   # sampled across all timed regions above (device-timed chains + e2e)
     checksum = float(h_spec[:1024].sum()) + float(h_fm[:1000].sum())
     for p in (hp, sp, fp):
         sdr.pinned_free(p)

@@ -58,6 +58,8 @@ struct b200sdr_ctx {
     /* workspaces (grown on demand) */
     float *d_partials = nullptr; size_t partials_floats = 0;
     float *d_env = nullptr; size_t env_floats = 0;
+    float *d_res_spec = nullptr, *d_res_fm = nullptr, *d_res_am = nullptr; /* batch_host result staging */
+    size_t res_spec_floats = 0, res_fm_floats = 0, res_am_floats = 0;
     uint8_t *d_wave[2] = {nullptr, nullptr}; size_t wave_bytes = 0;
     cudaEvent_t ev_wave_copied[2] = {nullptr, nullptr}, ev_wave_done[2] = {nullptr, nullptr};
 
@@ -527,7 +529,8 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     void *dev_ptrs[] = {ctx->d_ring, ctx->d_spec_buf, ctx->d_bounce, ctx->d_spec_acc, ctx->d_fm_buf, ctx->d_am_buf,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
-                        ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds};
+                        ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
+                        ctx->d_res_am};
     for (void *p : dev_ptrs) if (p) cudaFree(p);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -711,10 +714,11 @@ int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const uint8_t *iq_
     }
     const uint64_t fm_len = b200::wbfm_audio_len(len_each), am_len = b200::am_audio_len(len_each);
     float *d_spec = nullptr, *d_fm = nullptr, *d_am = nullptr;
-    /* per-wave result buffers, double buffered with the wave */
-    if (chains & B200SDR_CHAIN_SPECTRUM) CU(cudaMalloc((void **)&d_spec, 2 * per_wave * 1024 * sizeof(float)));
-    if (chains & B200SDR_CHAIN_WBFM) CU(cudaMalloc((void **)&d_fm, 2 * per_wave * fm_len * sizeof(float)));
-    if (chains & B200SDR_CHAIN_AM) CU(cudaMalloc((void **)&d_am, 2 * per_wave * am_len * sizeof(float)));
+    /* per-wave result buffers, double buffered with the wave; kept in the context between calls */
+    int rca = B200SDR_OK;
+    if (chains & B200SDR_CHAIN_SPECTRUM) { rca = ensure_floats(ctx, &ctx->d_res_spec, &ctx->res_spec_floats, 2 * per_wave * 1024); if (rca) return rca; d_spec = ctx->d_res_spec; }
+    if (chains & B200SDR_CHAIN_WBFM) { rca = ensure_floats(ctx, &ctx->d_res_fm, &ctx->res_fm_floats, 2 * per_wave * fm_len); if (rca) return rca; d_fm = ctx->d_res_fm; }
+    if (chains & B200SDR_CHAIN_AM) { rca = ensure_floats(ctx, &ctx->d_res_am, &ctx->res_am_floats, 2 * per_wave * am_len); if (rca) return rca; d_am = ctx->d_res_am; }
     int rc = B200SDR_OK;
     bool used[2] = {false, false};
     uint32_t wave = 0;
@@ -747,9 +751,6 @@ int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const uint8_t *iq_
         used[b] = true;
     }
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_copy), e2 = cudaStreamSynchronize(ctx->s_compute);
-    if (d_spec) cudaFree(d_spec);
-    if (d_fm) cudaFree(d_fm);
-    if (d_am) cudaFree(d_am);
     if (rc) return rc;
     if (e1 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "copy stream", e1);
     if (e2 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "compute stream", e2);

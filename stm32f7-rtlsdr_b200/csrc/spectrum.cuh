@@ -39,6 +39,9 @@
 #ifndef B200_SPEC_PREFETCH
 #define B200_SPEC_PREFETCH 1 /* issue the loads of frame m+1 before the FFT of frame m */
 #endif
+#ifndef B200_SPEC_FUSE_WIN
+#define B200_SPEC_FUSE_WIN 1 /* window multiply folded into the first butterfly stage of pass 1 */
+#endif
 #ifndef B200_SPEC_MERGE_TW
 #define B200_SPEC_MERGE_TW 1 /* fold the inter-pass twiddles into the first butterfly stage of pass 2 */
 #endif
@@ -81,10 +84,16 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     c2 *s_xp = reinterpret_cast<c2 *>(smem + B200_SPEC_SMEM_XP) + warp * (32 * B200_SPEC_XP);
 
-    /* stage window as win[t][j] = w[t + 32 j] and twiddles as tw[k1][t] = W1024^{t k1} */
+    /* stage the window per lane in the order pass 1 consumes it: win[t][2 i + h] = w[t + 32 (e_i + 16 h)]
+     * with e_i = bitrev5(2 i) -- the two samples of first-stage butterfly i sit side by side --
+     * and the twiddles as pairs (see below) */
     for (int i = tid; i < 1024; i += B200_SPEC_THREADS) {
         int t = i & 31, j = i >> 5;
-        s_win[t * B200_SPEC_WP + j] = __ldg(p.window + i);
+        {
+            const int e = j & 15, h = j >> 4;
+            const int bi = b200_bitrev5(e) >> 1; /* butterfly index i with bitrev5(2 i) == e */
+            s_win[t * B200_SPEC_WP + 2 * bi + h] = __ldg(p.window + i);
+        }
         float2 w = __ldg(p.twiddle + ((t * j) & 1023));
 #if B200_SPEC_MERGE_TW
         /* pair layout: [e][lane] = (W^{e lane}, W^{(e+16) lane}), e = 0..15: one 16-byte load feeds a
@@ -123,15 +132,25 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #pragma unroll
             for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m * 512u + 32 * j);
         }
-        /* convert + window, written to the bit-reversed slot pass 1 wants */
+        /* convert, window and first DIT stage of pass 1 in one go: butterfly i takes samples
+         * e = bitrev5(2 i) and e + 16:  X = a wa + b wb,  Y = a wa - b wb  (3 packed ops) */
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * j4);
-            const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+        for (int i2 = 0; i2 < 8; ++i2) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * i2);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = 4 * j4 + jj;
-                v[b200_bitrev5(j)] = c2_scale(c2_from_u8_lo(raw[j]), wj[jj]);
+            for (int ii = 0; ii < 2; ++ii) {
+                const int i = 2 * i2 + ii, e = b200_bitrev5(2 * i);
+                const c2 pa = c2_scale(c2_from_u8_lo(raw[e]), wv[2 * ii]);
+#if B200_SPEC_FUSE_WIN
+                const c2 b = c2_from_u8_lo(raw[e + 16]);
+                v[2 * i] = c2_fma_s(b, wv[2 * ii + 1], pa);
+                v[2 * i + 1] = c2_fma_s(b, -wv[2 * ii + 1], pa);
+#else
+                const c2 pb = c2_scale(c2_from_u8_lo(raw[e + 16]), wv[2 * ii + 1]);
+                v[2 * i] = c2_add(pa, pb);
+                v[2 * i + 1] = c2_sub(pa, pb);
+#endif
             }
         }
         if (B200_SPEC_PREFETCH && m + 1 < m_end) {
@@ -139,7 +158,10 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #pragma unroll
             for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src + 32 * j);
         }
-        b200_fft32(v); /* v[k1] = Y[k1] */
+        b200_stage_k<4, 0>::run(v);
+        b200_stage_k<8, 0>::run(v);
+        b200_stage_k<16, 0>::run(v);
+        b200_stage_k<32, 0>::run(v); /* v[k1] = Y[k1] */
 #if !B200_SPEC_MERGE_TW
 #pragma unroll
         for (int k1 = 1; k1 < 32; ++k1) {

@@ -371,3 +371,48 @@ def test_kernel_launch_counter_moves(sdr, g):
     before = sdr.kernel_launches()
     sdr.spectrum(g.synth(1, 262144, SYNTH_MULTITONE, 0))
     assert sdr.kernel_launches() >= before + 2
+
+
+# ------------------------------------------------------------------------------- more edge cases
+def test_empty_and_misaligned_batches(sdr, sdr_lib):
+    d = sdr.dev_alloc(4096)
+    try:
+        lib, ctx = sdr.lib, sdr.ctx
+        assert lib.b200sdr_batch_spectrum_dev(ctx, d, 0, 2048, d) == sdr_lib.OK          # no captures
+        assert lib.b200sdr_batch_wbfm_dev(ctx, d, 1, 0, d, None) == sdr_lib.OK           # empty capture
+        assert lib.b200sdr_batch_am_dev(ctx, d, 0, 0, d) == sdr_lib.OK
+        assert lib.b200sdr_batch_wbfm_dev(ctx, d, 1, 2044, d, None) == sdr_lib.NOT_SUPPORTED  # not 16-byte granular
+        assert lib.b200sdr_batch_am_dev(ctx, d + 4, 1, 2048, d) == sdr_lib.NOT_SUPPORTED      # misaligned pointer
+        assert lib.b200sdr_batch_spectrum_dev(ctx, d, 1, 2046, d) == sdr_lib.NOT_SUPPORTED    # multiple-of-4 rule
+    finally:
+        sdr.dev_free(d)
+
+
+def test_many_small_captures(sdr, g):
+    n_cap, len_each = 300, 4096
+    iq = g.synth(n_cap, len_each, SYNTH_WBFM, 500)
+    spec = sdr.spectrum(iq, n_cap)
+    fm = sdr.wbfm(iq, n_cap)
+    am = sdr.am(iq, n_cap)
+    for c in (0, 1, 149, 299):
+        blk = iq[c * len_each:(c + 1) * len_each]
+        spec_check_few_frames(spec[c], g.spectrum(blk)[0])
+        assert np.max(np.abs(fm[c] - g.wbfm(blk))) <= FM_AUDIO_ATOL
+        assert np.max(np.abs(am[c] - g.am(blk))) <= AM_AUDIO_ATOL
+
+
+def test_streaming_tiny_blocks(sdr_lib, g):
+    """Blocks far smaller than a frame or a FIR chunk (down to the 4-byte minimum)."""
+    total = 4 * 1500
+    iq = g.synth(1, total, SYNTH_WBFM, 77)
+    cuts = [4] * 300 + [8] * 100 + [12] * 50 + [4000 - 0]
+    cuts = cuts[:-1] + [total - sum(cuts[:-1])]
+    with sdr_lib.B200Sdr(slot_bytes=4096, ring_slots=3) as s:
+        feed(s, iq, cuts)
+        spec, frames = s.get_spectrum()
+        fm = s.get_audio(sdr_lib.CHAIN_WBFM)
+    gold, gframes = g.spectrum(iq)
+    assert frames == gframes == 4
+    spec_check_few_frames(spec, gold)
+    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
