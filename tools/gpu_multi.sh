@@ -1,8 +1,15 @@
 #!/bin/bash
-# 2-GPU check of the torchrun contract
+# N-GPU check of the torchrun contract (N from $NG)
+NG=${NG:-2}
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/multi_gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 --captures-per-gpu 128 --e2e-captures 16 > gpurun_out/bench_n2.txt 2>&1
-tail -c 2500 gpurun_out/bench_n2.txt
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.txt 2>&1
-tail -c 600 gpurun_out/bench_ref_n2.txt
+nvidia-smi -L | wc -l; cat /sys/devices/system/node/online; nproc
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG --steps 3 --warmup 3 > gpurun_out/bench_n$NG.txt 2> gpurun_out/bench_n$NG.err
+python - $NG <<'PY'
+import json,sys
+n=sys.argv[1]
+try:
+    d=json.loads([l for l in open(f'gpurun_out/bench_n{n}.txt').read().strip().splitlines() if l.startswith('{')][-1])
+    print('N',d['n_gpus'],'value', round(d['value']), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'clocks', d['clocks'])
+except Exception as e:
+    print('parse failed', e); print(open(f'gpurun_out/bench_n{n}.err').read()[-2000:])
+PY
