@@ -12,7 +12,8 @@
  *     stage 1: each sample feeds the 4 outputs y1[m] = sum g1[k] x[20 m - k] covering it
  *              (4 rotating packed accumulators; outputs 0..3 need the previous thread's 4
  *              tails, 4..9 complete in-chunk, 10..13 are this thread's tails)
- *     stage 2: y2[q] = sum_{k<120} g2[k] y1[10 q - k] out of a shared window with 119 history
+ *     stage 2: y2[q] = sum_{k<120} g2[k] y1[10 q - k], also in scatter form: the thread's ten y1
+ *              values (registers) feed 13 outputs; partial sums meet in a shared exchange tile
  *     envelope r[q] = |y2[q]|
  * Only FIRs are involved, so segments that start one tile early reproduce the single-segment
  * result bit for bit.  The DC blocker has a pole at 0.999 (memory ~ 1 s) and therefore runs in
@@ -36,10 +37,14 @@
 #define B200_AM_T3 48
 #define B200_AM_BHIST 24 /* b[] history needed by the resampler */
 
+#define B200_AM_NP 13                       /* a stage-1 chunk (10 outputs) reaches 13 stage-2 outputs */
+#define B200_AM_PP (B200_AM_THREADS + 12)   /* slots per row of the partial-sum exchange            */
+
 #define B200_AM_SM_RAW 0
-#define B200_AM_SM_TAIL (B200_AM_SM_RAW + B200_AM_TILE_BYTES)                    /* c2 [129][4]       */
-#define B200_AM_SM_Y1 (B200_AM_SM_TAIL + (B200_AM_THREADS + 1) * 4 * 8)          /* c2 [119 + 1280]   */
-#define B200_AM_SM_TAILC (B200_AM_SM_Y1 + (B200_AM_HIST + B200_AM_TILE_Y1 + 1) * 8) /* c2 [2][4]      */
+#define B200_AM_SM_TAIL (B200_AM_SM_RAW + B200_AM_TILE_BYTES)                    /* c2 [4][132]       */
+#define B200_AM_SM_PART (B200_AM_SM_TAIL + 4 * 132 * 8)                          /* c2 [13][140]      */
+#define B200_AM_SM_CARRY (B200_AM_SM_PART + B200_AM_NP * B200_AM_PP * 8)         /* c2 [13][12]       */
+#define B200_AM_SM_TAILC (B200_AM_SM_CARRY + B200_AM_NP * 12 * 8)                /* c2 [2][4]         */
 #define B200_AM_SM_BAR (B200_AM_SM_TAILC + 2 * 4 * 8)
 #define B200_AM_SMEM_BYTES (B200_AM_SM_BAR + 16)
 
@@ -52,8 +57,8 @@
 #endif
 
 struct AmFrontState {
-    float tail[8];                    /* 4 packed partial sums  */
-    float y1_hist[2 * B200_AM_HIST + 2]; /* y1[m0-119 .. m0-1]    */
+    float tail[8];                          /* stage 1: 4 packed partial sums carried to the next chunk */
+    float part[2 * B200_AM_NP * 12];        /* stage 2: partial sums of the next 12 outputs, [d][j]      */
 };
 struct AmBackState {
     float r_last, b_last;
@@ -65,9 +70,9 @@ struct AmTaps {
     float g2[B200_AM_T2];
     float g3[B200_AM_T3];
     float rho;
-    float rho4;           /* rho^4  */
-    float rho4_pow[6];    /* (rho^4)^(2^s) */
-    float rho_i[4];       /* rho^(i+1), i = 0..3 */
+    float rho4;           /* rho^PER: one thread of k_am_back */
+    float rho4_pow[6];    /* (rho^PER)^(2^s) */
+    float rho_i[16];      /* rho^(i+1), i = 0..PER-1 (PER = B200_AMB_PER <= 16) */
 };
 
 #ifdef B200_EMULATED
@@ -125,7 +130,8 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
     const AmTaps *taps = &c_am_taps;
     B200_DYN_SMEM(smem);
     c2 *s_tail = reinterpret_cast<c2 *>(smem + B200_AM_SM_TAIL);
-    c2 *s_y1 = reinterpret_cast<c2 *>(smem + B200_AM_SM_Y1);
+    c2 *s_part = reinterpret_cast<c2 *>(smem + B200_AM_SM_PART);
+    c2 *s_carry = reinterpret_cast<c2 *>(smem + B200_AM_SM_CARRY);
     c2 *s_tailc = reinterpret_cast<c2 *>(smem + B200_AM_SM_TAILC);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + B200_AM_SM_BAR);
 
@@ -148,10 +154,10 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
         if (p.state) { tr = p.state[capture].tail[2 * tid]; ti = p.state[capture].tail[2 * tid + 1]; }
         s_tailc[4 + tid] = c2_make(tr, ti);
     }
-    if (tid < B200_AM_HIST) {
+    for (int i = tid; i < B200_AM_NP * 12; i += B200_AM_THREADS) {
         float yr = 0.0f, yi = 0.0f;
-        if (p.state) { yr = p.state[capture].y1_hist[2 * tid]; yi = p.state[capture].y1_hist[2 * tid + 1]; }
-        s_y1[tid] = c2_make(yr, yi);
+        if (p.state) { yr = p.state[capture].part[2 * i]; yi = p.state[capture].part[2 * i + 1]; }
+        s_carry[i] = c2_make(yr, yi);
     }
 
     auto issue_tile = [&](uint32_t it) { /* thread 0 only; single raw buffer */
@@ -183,44 +189,79 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
         for (int i = 0; i < 4; ++i) acc[i] = c2_zero();
         const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_AM_SM_RAW + tid * (2 * B200_AM_CHUNK));
         b200_am_words<0>::run(raw, g, acc, head);
-        {
-            c2 *tail_dst = (tid == last) ? s_tailc + par * 4 : s_tail + (tid + 1) * 4;
+        if (tid == last) {
 #pragma unroll
-            for (int i = 10; i < 14; ++i) tail_dst[i - 10] = acc[i & 3];
+            for (int i = 10; i < 14; ++i) s_tailc[par * 4 + (i - 10)] = acc[i & 3];
+        } else {
+#pragma unroll
+            for (int i = 10; i < 14; ++i) s_tail[(i - 10) * 132 + tid + 1] = acc[i & 3];
         }
         __syncthreads(); /* S1: raw consumed, tails visible */
         if (tid == 0 && it + 1 < my_tiles) issue_tile(it + 1);
-        {
-            const c2 *tail_src = (tid == 0) ? s_tailc + (par ^ 1) * 4 : s_tail + tid * 4;
+        if (tid == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) head[i] = c2_add(head[i], tail_src[i]);
+            for (int i = 0; i < 4; ++i) head[i] = c2_add(head[i], s_tailc[(par ^ 1) * 4 + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) head[i] = c2_add(head[i], s_tail[i * 132 + tid]);
         }
-#pragma unroll
-        for (int i = 0; i < B200_AM_OPT; ++i) s_y1[B200_AM_HIST + tid * B200_AM_OPT + i] = head[i];
-        __syncthreads(); /* S2: y1 of the tile visible */
 
-        /* stage 2: thread t -> q = tile * 128 + t, centre y1 index 10 q = tile start + 10 t */
+        /* stage 2, scatter form again: this thread's ten y1 values (registers) feed the 13 outputs
+         * y2[t + d] = sum_k g2[k] y1[10 (t + d) - k], d = 0..12, with tap k = 10 d - i for value i.
+         * 120 packed FMAs per thread, no shared-memory reads of the inputs; the 13 partial sums go to
+         * row d, slot t + d of the exchange tile, output q then adds column q. */
         {
-            const c2 *win = s_y1 + B200_AM_HIST + tid * B200_AM_OPT;
-            c2 s0 = c2_zero(), s1 = c2_zero();
-#pragma unroll 8
-            for (int k = 0; k < B200_AM_T2; k += 2) {
-                s0 = c2_fma_s(win[-k], taps->g2[k], s0);
-                s1 = c2_fma_s(win[-k - 1], taps->g2[k + 1], s1);
+            c2 part[B200_AM_NP];
+#pragma unroll
+            for (int d = 0; d < B200_AM_NP; ++d) {
+                c2 a = c2_zero();
+#pragma unroll
+                for (int i = 0; i < B200_AM_OPT; ++i) {
+                    const int k = 10 * d - i;
+                    if (k >= 0 && k < B200_AM_T2) a = c2_fma_s(head[i], taps->g2[k], a);
+                }
+                part[d] = a;
+            }
+#pragma unroll
+            for (int d = 0; d < B200_AM_NP; ++d) s_part[d * B200_AM_PP + tid + d] = part[d];
+        }
+        __syncthreads(); /* S2: partial sums of the tile visible */
+        {
+            /* column tid: rows d <= tid come from this tile, rows d > tid from the carried partials */
+            c2 y = c2_zero();
+#pragma unroll
+            for (int d = 0; d < B200_AM_NP; ++d) {
+                const c2 v = (d <= tid) ? s_part[d * B200_AM_PP + tid] : s_carry[d * 12 + tid];
+                y = c2_add(y, v);
             }
             float yr, yi;
-            c2_get(c2_add(s0, s1), yr, yi);
+            c2_get(y, yr, yi);
             const uint64_t q = (uint64_t)tile * B200_AM_THREADS + (uint64_t)tid;
             if (store && q < p.q_count) p.env[(uint64_t)capture * p.env_stride + q] = sqrtf(fmaf(yr, yr, yi * yi));
         }
-        __syncthreads(); /* S3: window consumed */
-        /* y1 history for the next tile = the 119 values before the end of the valid part;
-         * two-step copy so a source slot is never overwritten before it is read */
-        c2 hv = c2_zero();
-        if (tid < B200_AM_HIST) hv = s_y1[(last + 1) * B200_AM_OPT + tid];
-        __syncthreads(); /* S4 */
-        if (tid < B200_AM_HIST) s_y1[tid] = hv;
-        /* next tile's S1/S2 order this write before its readers */
+        __syncthreads(); /* S3: carried partials consumed */
+        /* partial sums that belong to the next 12 outputs: slots last+1 .. last+12 of every row */
+        c2 nc[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * B200_AM_THREADS;
+            nc[r] = c2_zero();
+            if (i < B200_AM_NP * 12) {
+                const int d = i / 12, j = i - 12 * d;
+                const int q = last + 1 + j; /* tile-local index of the output this entry belongs to */
+                if (j < d) {
+                    if (q - d >= 0) nc[r] = s_part[d * B200_AM_PP + q];   /* written by thread q - d of this tile */
+                    else if (q < 12) nc[r] = s_carry[d * 12 + q];          /* short tile: still owed from before */
+                }
+            }
+        }
+        __syncthreads(); /* S4: old carry read before it is replaced */
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * B200_AM_THREADS;
+            if (i < B200_AM_NP * 12) s_carry[i] = nc[r];
+        }
+        /* the next tile's S1/S2 order these writes before their readers and before row d is rewritten */
     }
 
     if (p.state) {
@@ -232,19 +273,19 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
             p.state[capture].tail[2 * tid] = tr;
             p.state[capture].tail[2 * tid + 1] = ti;
         }
-        if (tid < B200_AM_HIST) {
+        for (int i = tid; i < B200_AM_NP * 12; i += B200_AM_THREADS) {
             float yr, yi;
-            c2_get(s_y1[tid], yr, yi);
-            p.state[capture].y1_hist[2 * tid] = yr;
-            p.state[capture].y1_hist[2 * tid + 1] = yi;
+            c2_get(s_carry[i], yr, yi);
+            p.state[capture].part[2 * i] = yr;
+            p.state[capture].part[2 * i + 1] = yi;
         }
     }
 }
 
 /* ---- back end: b[q] = r[q] - r[q-1] + rho b[q-1];  a[s] = sum_k g3[k] v[3 s - k], v[2 q] = b[q] ---- */
 #define B200_AMB_THREADS 256
-#define B200_AMB_PER 4
-#define B200_AMB_TILE (B200_AMB_THREADS * B200_AMB_PER) /* 1024 envelope samples per tile */
+#define B200_AMB_PER 16
+#define B200_AMB_TILE (B200_AMB_THREADS * B200_AMB_PER) /* 4096 envelope samples per tile */
 
 struct AmBackParams {
     const float *env;   /* [capture][env_stride]                                   */

@@ -118,7 +118,7 @@ inline void fill_am_taps(AmTaps &t)
     t.rho = (float)rho;
     t.rho4 = (float)rho4;
     for (int s = 0; s < 6; ++s) t.rho4_pow[s] = (float)std::pow(rho4, double(1 << s));
-    for (int i = 0; i < 4; ++i) t.rho_i[i] = (float)std::pow(rho, i + 1);
+    for (int i = 0; i < B200_AMB_PER; ++i) t.rho_i[i] = (float)std::pow(rho, i + 1);
 }
 
 inline void fill_twiddles(float2 *tw1024)

@@ -83,8 +83,10 @@ def test_wbfm_streaming_state_carry(emu, g):
     state = np.zeros(emu.emu_sizeof_fm_state(), np.uint8)
     rng = np.random.default_rng(1)
     pos, outa, outd = 0, [], []
+    small = [1, 1, 2, 1, 3, 4, 5, 1]  # launches shorter than the 49-sample history of stage 2
     while pos < nch:
-        k = int(min(nch - pos, rng.integers(1, 300)))
+        k = small.pop(0) if small else int(min(nch - pos, rng.integers(1, 300)))
+        k = int(min(k, nch - pos))
         a = np.zeros(k * 12 // 5 + 2, np.float32)
         d = np.zeros(k * 12, np.float32)
         na = C.c_uint32(0)
@@ -122,8 +124,10 @@ def test_am_streaming_state_carry(emu, g):
     bs = np.zeros(emu.emu_sizeof_am_back_state(), np.uint8)
     rng = np.random.default_rng(1)
     pos, outa = 0, []
+    small = [1, 1, 2, 1, 3, 11, 12, 13, 1, 5]  # launches shorter than the 12-output reach of stage 2
     while pos < nch:
-        k = int(min(nch - pos, rng.integers(1, 300)))
+        k = small.pop(0) if small else int(min(nch - pos, rng.integers(1, 300)))
+        k = int(min(k, nch - pos))
         a = np.zeros(k + 2, np.float32)
         na = C.c_uint32(0)
         emu.emu_am_stream(iq[pos * 400:].ctypes.data, k, pos, fs.ctypes.data, bs.ctypes.data, a.ctypes.data, C.byref(na))

@@ -114,6 +114,28 @@ __global__ void __launch_bounds__(512) k(float *out, long long *cyc, float seed)
                 asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
                 asm volatile("prmt.b32 %0, %0, %1, 0x7504;" : "+r"(iv[i]) : "r"(w));
             }
+        } else if (MODE == 21) { // I2F.U8 with loop-variant input: IADD + I2F.U8 + FADD per op
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float f;
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+                asm volatile("{ .reg .u8 b; cvt.u8.u32 b, %1; cvt.rn.f32.u8 %0, b; }" : "=f"(f) : "r"(iv[i]));
+                asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(f));
+            }
+        } else if (MODE == 22) { // same without the conversion (IADD + FADD only), the baseline to subtract
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(iv[i]) : "r"(w));
+                asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(x));
+            }
+        } else if (MODE == 23) { // I2F.U8 + FFMA2 1:1 (does the conversion unit run beside the FMA pipe?)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float f;
+                asm volatile("{ .reg .u8 b; cvt.u8.u32 b, %1; cvt.rn.f32.u8 %0, b; }" : "=f"(f) : "r"(iv[i]));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                iv[i] = __float_as_uint(f) + iv[i];
+            }
         } else if (MODE == 20) { // FFMA2 + LDS.32 conflict-free 2:1
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -174,5 +196,8 @@ int main()
     run<16>("FFMA + IADD 2:1", 12, 2.0 / 3);
     run<17>("FFMA2 scalar-bcast multiplier", 8, 2);
     run<20>("FFMA2 + LDS.32 2:1", 12, 4.0 / 3);
+    run<21>("IADD + I2F.U8 + FADD (x8)", 24, 0);
+    run<22>("IADD + FADD (x8) baseline", 16, 0);
+    run<23>("I2F.U8 + FFMA2 + IADD (x8)", 24, 0);
     return 0;
 }
