@@ -100,3 +100,16 @@ def test_shard_ranges_cover_batch(sdr_lib):
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
     assert sh.all_shards(4096, 8)[3] == (1536, 2048)  # 512 captures per GPU on the 8-GPU box
+
+
+def test_example_host_driver_builds_and_refuses_without_gpu(sdr_lib, tmp_path):
+    """examples/host_driver.c is the C host driver of INTEGRATION.md: it must compile as plain C
+    against the header and link against the library (run for real by the GPU suite)."""
+    import subprocess
+    exe = tmp_path / "host_driver"
+    libdir = os.path.dirname(sdr_lib.LIB_PATH)
+    subprocess.run(["gcc", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "host_driver.c"),
+                    "-L", libdir, "-lb200sdr", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    if not HAVE_GPU:
+        res = subprocess.run([str(exe), "--synthetic", "wbfm", "100000"], capture_output=True, text=True, cwd=tmp_path)
+        assert res.returncode == 4 and "CUDA sm_100 device is required" in res.stderr

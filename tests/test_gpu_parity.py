@@ -416,3 +416,25 @@ def test_streaming_tiny_blocks(sdr_lib, g):
     spec_check_few_frames(spec, gold)
     n_fm = -(-((total // 2 // 120) * 12) // 5)
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
+
+
+def test_example_host_driver_runs(sdr_lib, g, tmp_path):
+    """The C host driver (examples/host_driver.c): reference START/WAIT/COMPLETE cadence over the
+    pinned ring; its audio files must equal the golden chains."""
+    import subprocess
+    exe = tmp_path / "host_driver"
+    libdir = os.path.dirname(sdr_lib.LIB_PATH)
+    subprocess.run(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "host_driver.c"),
+                    "-L", libdir, "-lb200sdr", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    total = 2_400_000
+    res = subprocess.run([str(exe), "--synthetic", "wbfm", str(total), "65024"], capture_output=True, text=True, cwd=tmp_path, check=True)
+    assert f"{total} bytes in" in res.stdout and "frames averaged" in res.stdout
+    iq = g.synth(1, total, SYNTH_WBFM, 0)
+    fm = np.fromfile(tmp_path / "fm48k.f32", np.float32)
+    am = np.fromfile(tmp_path / "am8k.f32", np.float32)
+    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_am = (2 * (total // 2 // 200) + 2) // 3
+    assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
+    assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
+    # the strongest bin is the +50 kHz carrier: bin round(50e3 / 2.4e6 * 1024) = 21
+    assert "bin   21" in res.stdout.split("\n")[1] or "bin   22" in res.stdout.split("\n")[1]
