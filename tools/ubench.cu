@@ -183,7 +183,6 @@ int main()
     run<4>("PRMT", 8, 0);
     run<3>("FFMA2 + PRMT 1:1", 16, 1);
     run<7>("FFMA + PRMT 1:1", 16, 0.5);
-    run<5>("I2F.U8 (+FADD)", 8, 0);
     run<10>("LDS.64", 8, 0);
     run<6>("FFMA2 + LDS.64 1:1", 16, 1);
     run<11>("MUFU.RCP (+FADD)", 16, 0);
