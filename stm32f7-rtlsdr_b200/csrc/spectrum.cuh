@@ -170,13 +170,15 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
             v[k1] = c2_cmul(v[k1], wr, wi);
         }
 #endif
-        /* transpose through the warp-private tile: row = k1 (the reader's lane), column = source lane t */
+        /* transpose through the warp-private tile: row = k1 (the reader's lane), column = source lane t.
+         * The barrier that keeps this frame's stores behind the previous frame's loads sits HERE, a whole
+         * pass later than those loads, so it never waits on them. */
+        __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) s_xp[k1 * B200_SPEC_XP + lane] = v[k1];
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 32; ++t) v[b200_bitrev5(t)] = s_xp[lane * B200_SPEC_XP + t];
-        __syncwarp();
 #if B200_SPEC_MERGE_TW
         /* first DIT stage of pass 2 with the four-step twiddles folded in: slots (2i, 2i+1) hold the
          * elements e = bitrev5(2i) < 16 and e + 16 of this lane's column; X = Ta a + Tb b, Y = Ta a - Tb b

@@ -9,7 +9,7 @@ import json
 try:
     d=json.loads(open('gpurun_out/bench_small.txt').read().strip().splitlines()[-1])
     print('value', round(d['value']), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), 'clocks', d['clocks'])
-    for k,v in d['chains'].items(): print(k, {a: round(b,4) for a,b in v.items()})
+    for k,v in d['chains'].items(): print(k, {a: round(b,4) for a,b in v.items() if isinstance(b, float)})
 except Exception as e:
     print('bench parse failed', e); print(open('gpurun_out/bench_small.txt').read()[-3000:])
 PY
