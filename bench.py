@@ -335,7 +335,10 @@ def main():
                          "traffic": 1.0074 * 2.0 * B * CAPTURE_SAMPLES,  # bytes per launch: ncu dram read+write = 1.0074 x algorithmic (profiles/r1_ncu_summary_v2.txt)
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": 2.0,
-                         "note": "FP32-pipe bound, not HBM bound: ~2100 fp32 lane-ops per 512 new samples (DESIGN.md)"},
+                         "note": "FP32-pipe bound, not HBM bound (DESIGN.md 5.1): 1028 FP32-pipe cycles per 1024-pt frame per SM "
+                                 "sub-partition for 512 new samples",
+                         "fp32_ceiling_GBps": 2.0 * 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * 512 / 1028 / 1e9,
+                         "frac_of_fp32_ceiling": spec_gbs / (2.0 * 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * 512 / 1028 / 1e9)},
             "chains": {
                 "spectrum": {"ms_per_step": ms_spec / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_spec * 1e-3) / 1e6,
                              "GBps": spec_gbs, "hbm_frac": spec_gbs / hbm_peak},
