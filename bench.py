@@ -258,6 +258,21 @@ def main():
     sdr.sync()
     ms_am = timed(4, args.steps)
 
+    # K2 alone (u8 -> cf32, 2 B in + 8 B out per sample): the one HBM-bound kernel of the path, as a
+    # reference for what the memory system gives this access pattern
+    Bc = min(B, 48)
+    cf = torch.empty(Bc * CAPTURE_BYTES, dtype=torch.float32, device="cuda")
+    conv = sdr.lib.b200sdr_convert_cf32_dev
+    for _ in range(2):
+        conv(sdr.ctx, iq.data_ptr(), Bc * CAPTURE_BYTES, 0, cf.data_ptr())
+    barrier()
+    sdr.timer_start()
+    for _ in range(args.steps):
+        conv(sdr.ctx, iq.data_ptr(), Bc * CAPTURE_BYTES, 0, cf.data_ptr())
+    ms_conv = max_over_ranks(sdr.timer_stop_ms())
+    conv_gbs = 10.0 * Bc * CAPTURE_SAMPLES * args.steps / (ms_conv * 1e-3) / 1e9
+    del cf
+
     samples_step = B * CAPTURE_SAMPLES * world              # whole job, per step
     value = samples_step * args.steps / (ms_total * 1e-3) / 1e6
     hbm_peak, peak_src = load_peaks()
@@ -344,6 +359,9 @@ def main():
                              "GBps": spec_gbs, "hbm_frac": spec_gbs / hbm_peak},
                 "wbfm": {"ms_per_step": ms_fm / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_fm * 1e-3) / 1e6,
                          "GBps": fm_gbs, "hbm_frac": fm_gbs / hbm_peak, "algorithmic_bytes_per_sample": fm_bytes},
+                "convert_cf32": {"ms_per_step": ms_conv / args.steps, "MSps_per_gpu": Bc * CAPTURE_SAMPLES * args.steps / (ms_conv * 1e-3) / 1e6,
+                                 "GBps": conv_gbs, "hbm_frac": conv_gbs / hbm_peak, "algorithmic_bytes_per_sample": 10.0,
+                                 "note": "K2 alone over %d captures: HBM-bound reference, not part of `value`" % Bc},
                 "am": {"ms_per_step": ms_am / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e6,
                        "GBps": am_gbs, "hbm_frac": am_gbs / hbm_peak, "algorithmic_bytes_per_sample": am_bytes,
                        "note": "config[3], secondary; not part of `value`"},

@@ -766,9 +766,9 @@ int32_t b200sdr_convert_cf32_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64
         return fail(ctx, B200SDR_NOT_SUPPORTED, "device conversion needs len % 16 == 0 and 16-byte aligned pointers");
     if (len == 0) return B200SDR_OK;
     DeviceGuard guard(ctx->device);
-    const uint64_t n16 = len / 16;
+    const uint64_t n_words = len / 4;
     const float *w = window == B200SDR_WINDOW_RECT ? nullptr : ctx->d_window[window];
-    k_convert_cf32<<<(unsigned)((n16 + 255) / 256), 256, 0, ctx->s_compute>>>((const uint4 *)iq_dev, (float4 *)out_dev, n16, w);
+    k_convert_cf32<<<(unsigned)((n_words + 1023) / 1024), 256, 0, ctx->s_compute>>>((const uint32_t *)iq_dev, (float4 *)out_dev, n_words, w);
     CU(cudaGetLastError());
     ctx->launches += 1;
     return B200SDR_OK;

@@ -9,36 +9,37 @@
 #include "cplx2.cuh"
 
 /* K2: out[2n] = (I_n - 127.5) w[n mod 1024], out[2n+1] = (Q_n - 127.5) w[n mod 1024].
- * One thread per 16 input bytes (8 complex samples): one 16-byte load, four 16-byte stores,
- * fully coalesced.  With window == nullptr the conversion is exact and unscaled (bit-exact parity
- * row of SURVEY.md section 8a).  `n16` = number of whole 16-byte groups; the host handles no tail
- * because the staging buffers are padded to 16 bytes. */
-__global__ void __launch_bounds__(256) k_convert_cf32(const uint4 *__restrict__ in, float4 *__restrict__ out,
-                                                      uint64_t n16, const float *__restrict__ window)
+ * A thread converts four 32-bit words (2 complex samples each) taken 256 words apart, so every warp
+ * load is 128 contiguous bytes and every warp store 512 contiguous bytes (whole sectors, no partial
+ * writes); streaming cache hints: the data is touched once.  With window == nullptr the conversion
+ * is exact and unscaled (bit-exact parity row of SURVEY.md section 8a).  `n_words` = len / 4. */
+__global__ void __launch_bounds__(256) k_convert_cf32(const uint32_t *__restrict__ in, float4 *__restrict__ out,
+                                                      uint64_t n_words, const float *__restrict__ window)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;
-    if (i >= n16) return;
-    const uint4 r = in[i];
-    float w[8];
-    if (window) {
-        const float4 *wp = reinterpret_cast<const float4 *>(window + ((i * 8u) & 1023u));
-        const float4 a = __ldg(wp), b = __ldg(wp + 1);
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = 1.0f;
-    }
-    const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+    const uint64_t base = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
+    uint32_t wd[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        const uint64_t j = base + 256u * k;
+        wd[k] = j < n_words ? __ldcs(in + j) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t j = base + 256u * k;
+        if (j >= n_words) continue;
+        float w0 = 1.0f, w1 = 1.0f;
+        if (window) {
+            const float2 ww = __ldg(reinterpret_cast<const float2 *>(window + ((j * 2u) & 1023u)));
+            w0 = ww.x;
+            w1 = ww.y;
+        }
         float4 o;
         /* __fmul_rn: keep the product a plain rounded multiply (nothing to contract with) */
-        o.x = __fmul_rn(b200_u8_to_f32(wd[k], 0), w[2 * k]);
-        o.y = __fmul_rn(b200_u8_to_f32(wd[k], 1), w[2 * k]);
-        o.z = __fmul_rn(b200_u8_to_f32(wd[k], 2), w[2 * k + 1]);
-        o.w = __fmul_rn(b200_u8_to_f32(wd[k], 3), w[2 * k + 1]);
-        out[i * 4u + k] = o;
+        o.x = __fmul_rn(b200_u8_to_f32(wd[k], 0), w0);
+        o.y = __fmul_rn(b200_u8_to_f32(wd[k], 1), w0);
+        o.z = __fmul_rn(b200_u8_to_f32(wd[k], 2), w1);
+        o.w = __fmul_rn(b200_u8_to_f32(wd[k], 3), w1);
+        __stcs(out + j, o);
     }
 }
 
