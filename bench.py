@@ -99,6 +99,16 @@ def cpu_reference(threads, target_seconds):
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     from oracle_api import Golden, SYNTH_WBFM
     g = Golden(f32=True)
+    # the ingest copy is the one part of the path the reference implements: time ITS code when
+    # the reference build (oracle/_ref, made from /root/reference by oracle/Makefile) is present
+    copy_impl = "restated USB_ReadPacket (oracle/golden.c)"
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_ingest.so")
+    if os.path.exists(ref_so):
+        ref = C.CDLL(ref_so)
+        g.lib.gold_set_ingest_hook.argtypes = [C.c_void_p]
+        g.lib.gold_set_ingest_hook(C.cast(ref.ref_copy_block, C.c_void_p))
+        g._ref_keepalive = ref
+        copy_impl = "the reference's own USB_ReadPacket (oracle/_ref)"
     n_each = 2_400_000
     probe = g.synth(1, 2 * n_each, SYNTH_WBFM, 0)
     t1 = g.lib.gold_time_spectrum(probe.ctypes.data, n_each, 1, 1, 1)
@@ -111,7 +121,7 @@ def cpu_reference(threads, target_seconds):
     tf = g.lib.gold_time_wbfm(data.ctypes.data, n_each, distinct, n_blocks, threads)
     samples = n_blocks * n_each
     return {"value": samples / (ts + tf) / 1e6, "unit": "MS/s", "cores": threads, "kind": "port",
-            "sample": f"{n_blocks} x 1 s captures (2.4 M samples each) through spectrum + WBFM, oracle/golden.c fp32 build, {threads} threads",
+            "sample": f"{n_blocks} x 1 s captures (2.4 M samples each) through ingest copy [{copy_impl}] + spectrum + WBFM [oracle/golden.c fp32 build], {threads} threads",
             "spectrum_MSps": samples / ts / 1e6, "wbfm_MSps": samples / tf / 1e6, "seconds": ts + tf}
 
 
@@ -372,6 +382,7 @@ def main():
         print(json.dumps(line))
     sdr.close()
     if world > 1:
+        dist.barrier()   # rank 0 also ran the ingest probe; leave together
         dist.destroy_process_group()
 
 

@@ -451,6 +451,11 @@ typedef struct {
     const uint8_t *iq; size_t n_each; uint32_t n_distinct, n_blocks; int tid, threads; int kind; double checksum;
 } work_t;
 
+/* optional: the reference's OWN copy routine (oracle/_ref ref_copy_block), installed by bench.py when
+ * the reference build is present; otherwise the restatement gold_ingest_copy is used */
+static size_t (*g_ingest_hook)(uint8_t *, const uint8_t *, size_t);
+void gold_set_ingest_hook(size_t (*fn)(uint8_t *, const uint8_t *, size_t)) { g_ingest_hook = fn; }
+
 static void *worker(void *arg)
 {
     work_t *w = (work_t *)arg;
@@ -462,10 +467,12 @@ static void *worker(void *arg)
     real *o = (real *)malloc(sizeof(real) * (out_len + 1));
     for (uint32_t b = (uint32_t)w->tid; b < w->n_blocks; b += (uint32_t)w->threads) {
         const uint8_t *src = w->iq + (size_t)(b % w->n_distinct) * bytes;
-        for (size_t off = 0; off < bytes; off += 512) {
-            size_t l = bytes - off < 512 ? bytes - off : 512;
-            gold_ingest_copy(buf + off, src + off, (uint16_t)l);
-        }
+        if (g_ingest_hook) g_ingest_hook(buf, src, bytes);
+        else
+            for (size_t off = 0; off < bytes; off += 512) {
+                size_t l = bytes - off < 512 ? bytes - off : 512;
+                gold_ingest_copy(buf + off, src + off, (uint16_t)l);
+            }
         if (w->kind == 0) gold_spectrum(buf, w->n_each, GOLD_WIN_HANN, GOLD_AVG_MEAN, 0.0, o);
         else if (w->kind == 1) gold_wbfm(buf, w->n_each, o, NULL);
         else gold_am(buf, w->n_each, o);

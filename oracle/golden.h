@@ -87,6 +87,7 @@ void gold_synth_fill(uint8_t *iq, uint32_t n_captures, uint64_t len_each, uint32
 
 /* ---- CPU baseline timing helpers: n_blocks blocks of n_each complex samples (block b reads
  * distinct buffer b % n_distinct) over `threads` POSIX threads; returns wall seconds ---- */
+void gold_set_ingest_hook(size_t (*fn)(uint8_t *, const uint8_t *, size_t)); /* NULL = restated copy */
 double gold_time_spectrum(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads);
 double gold_time_wbfm(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads);
 double gold_time_am(const uint8_t *iq, size_t n_each, uint32_t n_distinct, uint32_t n_blocks, int threads);

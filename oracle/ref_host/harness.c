@@ -56,6 +56,22 @@ uint32_t ref_read_packet(uint8_t *dest, const uint8_t *src, uint16_t len)
     return written;
 }
 
+/* A whole block through the reference's own copy routine, one max-size packet (512 bytes,
+ * USB_EPA_MAXPKT, usbh_rtlsdr.c:830) at a time, as HCD_RXQLVL_IRQHandler feeds it (hal_hcd.c:1108-1112).
+ * Thread-safe (the FIFO cursor is thread-local); used by bench.py's CPU baseline so that the part of
+ * the path the reference DOES implement is timed with the reference's code.  Returns bytes written. */
+size_t ref_copy_block(uint8_t *dest, const uint8_t *src, size_t nbytes)
+{
+    size_t off = 0;
+    while (off < nbytes) {
+        uint16_t n = (uint16_t)(nbytes - off < 512 ? nbytes - off : 512);
+        ref_fifo_set_source(src + off);
+        USB_ReadPacket((USB_OTG_GlobalTypeDef *)0, dest + off, n);
+        off += n;
+    }
+    return (off + 3) & ~(size_t)3;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * 2. stubs and glue
  * ------------------------------------------------------------------------------------------- */

@@ -15,23 +15,27 @@
 
 #include "stm32f7xx_hal.h"
 
-static const uint8_t *g_fifo_src;   /* next byte the "FIFO" will deliver */
-static uint32_t g_fifo_word;        /* backing store for the popped word */
-static uint64_t g_fifo_pops;
+/* thread-local: bench.py's CPU baseline runs the reference copy on every host core at once */
+static __thread const uint8_t *g_fifo_src; /* next byte the "FIFO" will deliver */
+static __thread uint64_t g_fifo_pops;
 
 void ref_fifo_set_source(const uint8_t *src) { g_fifo_src = src; }
 uint64_t ref_fifo_pops(void) { return g_fifo_pops; }
 const uint8_t *ref_fifo_cursor(void) { return g_fifo_src; }
 
-volatile uint32_t *ref_fifo_next(void)
+/* one FIFO pop = the next whole 32-bit word of the stream (the tail of a short packet is padding).
+ * Kept inline so the copy loop of USB_ReadPacket costs what a register read would, not a call. */
+typedef uint32_t __attribute__((aligned(1), may_alias)) ref_u32_unaligned;
+static inline uint32_t ref_fifo_pop(void)
 {
-    memcpy(&g_fifo_word, g_fifo_src, 4); /* FIFO words are whole: the tail of a short packet is padding */
+    uint32_t w = *(const ref_u32_unaligned *)g_fifo_src;
     g_fifo_src += 4;
     g_fifo_pops++;
-    return &g_fifo_word;
+    return w;
 }
+static __thread uint32_t g_fifo_sink; /* target of FIFO writes (USB_WritePacket is never exercised) */
 
 #undef USBx_DFIFO
-#define USBx_DFIFO(i) (*ref_fifo_next())
+#define USBx_DFIFO(i) (*((void)(i), (g_fifo_sink = ref_fifo_pop()), (volatile uint32_t *)&g_fifo_sink))
 
 #include REF_LL_USB_C
