@@ -29,10 +29,13 @@
 #endif
 
 #if defined(__CUDA_ARCH__) && !defined(B200_EMULATED)
-#define B200_PACKED 1
+#define B200_PACKED 1 /* real device code (inline PTX allowed) */
+#if !defined(B200_SCALAR_MATH) || !B200_SCALAR_MATH
+#define B200_PACKED_MATH 1 /* complex numbers as fp32x2 pairs; -DB200_SCALAR_MATH=1 is the A/B knob */
+#endif
 #endif
 
-#ifdef B200_PACKED
+#ifdef B200_PACKED_MATH
 
 struct c2 { unsigned long long v; };
 
