@@ -50,6 +50,28 @@ typedef struct b200sdr_e4k_pll {
 /* Returns the synthesised LO in Hz (0 if fosc is outside 16..30 MHz) and fills *out. */
 B200SDR_API uint32_t b200sdr_e4k_pll_params(uint32_t fosc, uint32_t intended_flo, b200sdr_e4k_pll *out);
 
+/* E4000 analog selection that follows the PLL in E4K_tune_params (RTL/Src/tuner_e4k.c:813-903):
+ * which band, which of the 16 RF tracking filters, and which IF filter settings (hence what analog
+ * passband the captured spectrum really has).  Values are enum e4k_band / enum e4k_if_filter of
+ * RTL/Inc/tuner_e4k.h. */
+#define B200SDR_E4K_BAND_VHF2 0
+#define B200SDR_E4K_BAND_VHF3 1
+#define B200SDR_E4K_BAND_UHF  2
+#define B200SDR_E4K_BAND_L    3
+#define B200SDR_E4K_IF_FILTER_MIX  0
+#define B200SDR_E4K_IF_FILTER_CHAN 1
+#define B200SDR_E4K_IF_FILTER_RC   2
+
+/* Band for a synthesised LO: the thresholds of E4K_tune_params state 4 (tuner_e4k.c:871-878). */
+B200SDR_API int32_t b200sdr_e4k_band(uint32_t flo_hz);
+/* 4-bit RF filter index: choose_rf_filter (tuner_e4k.c:250-277) -- 0 on the VHF bands and for an
+ * unknown band, else the first closest centre of the UHF / L table (:218-229). */
+B200SDR_API int32_t b200sdr_e4k_rf_filter(int32_t band, uint32_t freq_hz);
+/* Register index of the IF filter setting closest to bw_hz: find_if_bw (tuner_e4k.c:363-372) over
+ * the mixer / channel / RC bandwidth tables (:165-191); 0 for an unknown filter.  *actual_hz (may be
+ * NULL) receives the bandwidth that index selects (0 for an unknown filter). */
+B200SDR_API int32_t b200sdr_e4k_if_bw_index(int32_t filter, uint32_t bw_hz, uint32_t *actual_hz);
+
 #ifdef __cplusplus
 }
 #endif

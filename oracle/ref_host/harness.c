@@ -40,6 +40,10 @@
 /* ---- from ll_usb_shim.c ---- */
 void ref_fifo_set_source(const uint8_t *src);
 uint64_t ref_fifo_pops(void);
+/* e4k_wrap.c: the reference's file-static E4000 selection routines */
+int ref_e4k_rf_filter(int band, uint32_t freq);
+int ref_e4k_if_bw_index(int filter, uint32_t bw);
+uint32_t ref_e4k_if_bw_hz(int filter, int idx);
 const uint8_t *ref_fifo_cursor(void);
 
 /* ---------------------------------------------------------------------------------------------
@@ -346,6 +350,15 @@ static int cli_frontend(int argc, char **argv)
         uint32_t o[8];
         uint32_t flo = ref_e4k_pll((uint32_t)strtoul(argv[2], 0, 0), (uint32_t)strtoul(argv[3], 0, 0), o);
         printf("REF_E4K %u %u %u %u %u %u %u %u %u\n", flo, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+        return 0;
+    }
+    if (strcmp(argv[1], "--e4k-rf") == 0 && argc >= 4) { /* e4k_wrap.c -> choose_rf_filter */
+        printf("REF_E4K_RF %d\n", ref_e4k_rf_filter(atoi(argv[2]), (uint32_t)strtoul(argv[3], 0, 0)));
+        return 0;
+    }
+    if (strcmp(argv[1], "--e4k-ifbw") == 0 && argc >= 4) { /* e4k_wrap.c -> find_if_bw */
+        int idx = ref_e4k_if_bw_index(atoi(argv[2]), (uint32_t)strtoul(argv[3], 0, 0));
+        printf("REF_E4K_IFBW %d %u\n", idx, ref_e4k_if_bw_hz(atoi(argv[2]), idx));
         return 0;
     }
     return -1;

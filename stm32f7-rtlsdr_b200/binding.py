@@ -177,6 +177,30 @@ def e4k_pll_params(fosc, intended_flo):
     return flo, (p.fosc, p.intended_flo, p.flo, p.x, p.z, p.r, p.r_idx, p.threephase)
 
 
+def e4k_band(flo_hz):
+    lib = load_library()
+    lib.b200sdr_e4k_band.restype = C.c_int32
+    lib.b200sdr_e4k_band.argtypes = [C.c_uint32]
+    return lib.b200sdr_e4k_band(flo_hz)
+
+
+def e4k_rf_filter(band, freq_hz):
+    lib = load_library()
+    lib.b200sdr_e4k_rf_filter.restype = C.c_int32
+    lib.b200sdr_e4k_rf_filter.argtypes = [C.c_int32, C.c_uint32]
+    return lib.b200sdr_e4k_rf_filter(band, freq_hz)
+
+
+def e4k_if_bw_index(filt, bw_hz):
+    """-> (register index, bandwidth in Hz that index selects)"""
+    lib = load_library()
+    lib.b200sdr_e4k_if_bw_index.restype = C.c_int32
+    lib.b200sdr_e4k_if_bw_index.argtypes = [C.c_int32, C.c_uint32, C.POINTER(C.c_uint32)]
+    hz = C.c_uint32(0)
+    idx = lib.b200sdr_e4k_if_bw_index(filt, bw_hz, C.byref(hz))
+    return idx, hz.value
+
+
 def _u8(a):
     a = np.ascontiguousarray(a, dtype=np.uint8)
     return a

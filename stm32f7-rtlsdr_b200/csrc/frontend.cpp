@@ -93,4 +93,70 @@ uint32_t b200sdr_e4k_pll_params(uint32_t fosc, uint32_t intended_flo, b200sdr_e4
     return flo;
 }
 
+/* E4K_tune_params state 4, RTL/Src/tuner_e4k.c:871-878 */
+int32_t b200sdr_e4k_band(uint32_t flo_hz)
+{
+    if (flo_hz < 140000000u) return B200SDR_E4K_BAND_VHF2;
+    if (flo_hz < 350000000u) return B200SDR_E4K_BAND_VHF3;
+    if (flo_hz < 1135000000u) return B200SDR_E4K_BAND_UHF;
+    return B200SDR_E4K_BAND_L;
+}
+
+namespace {
+/* closest_arr_idx, tuner_e4k.c:231-247: strict '<' keeps the FIRST entry on a tie.  Tables in kHz. */
+int32_t nearest_khz_entry(const uint32_t *khz, int n, uint32_t hz)
+{
+    int32_t best = 0;
+    uint32_t best_gap = 0xFFFFFFFFu;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t entry = khz[i] * 1000u;
+        const uint32_t gap = hz > entry ? hz - entry : entry - hz;
+        if (gap < best_gap) {
+            best_gap = gap;
+            best = i;
+        }
+    }
+    return best;
+}
+const uint32_t kRfCentreUhfKhz[16] = {360000, 380000, 405000, 425000, 450000, 475000, 505000, 540000,
+                                      575000, 615000, 670000, 720000, 760000, 840000, 890000, 970000};
+const uint32_t kRfCentreLKhz[16] = {1300000, 1320000, 1360000, 1410000, 1445000, 1460000, 1490000, 1530000,
+                                    1560000, 1590000, 1640000, 1660000, 1680000, 1700000, 1720000, 1750000};
+const uint32_t kMixBwKhz[16] = {27000, 27000, 27000, 27000, 27000, 27000, 27000, 27000,
+                                4600,  4200,  3800,  3400,  3300,  2700,  2300,  1900};
+const uint32_t kChanBwKhz[32] = {5500, 5300, 5000, 4800, 4600, 4400, 4300, 4100, 3900, 3800, 3700,
+                                 3600, 3400, 3300, 3200, 3100, 3000, 2950, 2900, 2800, 2750, 2700,
+                                 2600, 2550, 2500, 2450, 2400, 2300, 2280, 2240, 2200, 2150};
+const uint32_t kRcBwKhz[16] = {21400, 21000, 17600, 14700, 12400, 10600, 9000, 7700,
+                               6400,  5300,  4400,  3400,  2600,  1800,  1200, 1000};
+} // namespace
+
+/* choose_rf_filter, tuner_e4k.c:250-277 over the centre tables :218-229 */
+int32_t b200sdr_e4k_rf_filter(int32_t band, uint32_t freq_hz)
+{
+    if (band == B200SDR_E4K_BAND_UHF) return nearest_khz_entry(kRfCentreUhfKhz, 16, freq_hz);
+    if (band == B200SDR_E4K_BAND_L) return nearest_khz_entry(kRfCentreLKhz, 16, freq_hz);
+    return 0;
+}
+
+/* find_if_bw, tuner_e4k.c:363-372 over mix_filter_bw / ifch_filter_bw / ifrc_filter_bw :165-191 */
+int32_t b200sdr_e4k_if_bw_index(int32_t filter, uint32_t bw_hz, uint32_t *actual_hz)
+{
+    const uint32_t *table = nullptr;
+    int n = 0;
+    switch (filter) {
+    case B200SDR_E4K_IF_FILTER_MIX: table = kMixBwKhz; n = 16; break;
+    case B200SDR_E4K_IF_FILTER_CHAN: table = kChanBwKhz; n = 32; break;
+    case B200SDR_E4K_IF_FILTER_RC: table = kRcBwKhz; n = 16; break;
+    default: break;
+    }
+    if (!table) {
+        if (actual_hz) *actual_hz = 0;
+        return 0;
+    }
+    const int32_t idx = nearest_khz_entry(table, n, bw_hz);
+    if (actual_hz) *actual_hz = table[idx] * 1000u;
+    return idx;
+}
+
 } /* extern "C" */

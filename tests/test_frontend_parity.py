@@ -86,3 +86,58 @@ def test_e4k_pll_bit_exact_against_reference(b):
 def test_e4k_kat_at_the_firmware_frequency(b):
     flo, (fosc, want, got, x, z, r, r_idx, three) = b.e4k_pll_params(28800000, 99700000)
     assert (flo, got, x, z, r, r_idx, three) == (99699993, 99699993, 50972, 110, 32, 13, 1)
+
+
+# ---- E4000 band / RF filter / IF bandwidth selection (tuner_e4k.c:218-277, :363-372, :871-878) ----
+
+def test_e4k_band_thresholds(b):
+    # E4K_tune_params state 4 (tuner_e4k.c:871-878): < 140 MHz VHF2, < 350 MHz VHF3, < 1135 MHz UHF, else L
+    for hz, band in ((50000000, 0), (139999999, 0), (140000000, 1), (349999999, 1), (350000000, 2),
+                     (1134999999, 2), (1135000000, 3), (2200000000, 3)):
+        assert b.e4k_band(hz) == band, hz
+    assert b.e4k_band(99699993) == 0  # the LO the firmware really gets for 99.7 MHz
+
+
+def test_e4k_selection_kats(b):
+    assert b.e4k_rf_filter(0, 99700000) == 0 and b.e4k_rf_filter(1, 200000000) == 0
+    assert b.e4k_rf_filter(2, 433920000) == 3       # 425 MHz centre
+    assert b.e4k_rf_filter(2, 370000000) == 0       # tie 360/380 -> first
+    assert b.e4k_rf_filter(3, 1575420000) == 9      # GPS L1: 14.58 MHz from 1590, 15.42 from 1560
+    assert b.e4k_rf_filter(7, 1575420000) == 0      # unknown band
+    # the bandwidth the firmware asks for (RTLSDR_Handle->bw) against the three IF filters
+    assert b.e4k_if_bw_index(0, 2400000) == (14, 2300000)
+    assert b.e4k_if_bw_index(1, 2400000) == (26, 2400000)
+    assert b.e4k_if_bw_index(2, 2400000) == (12, 2600000)
+    assert b.e4k_if_bw_index(0, 27000000) == (0, 27000000)   # eight equal entries -> first
+    assert b.e4k_if_bw_index(5, 2400000) == (0, 0)
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+def test_e4k_selection_bit_exact_against_reference(b):
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_ingest.so"))
+    lib.ref_e4k_rf_filter.argtypes = [C.c_int, C.c_uint32]
+    lib.ref_e4k_if_bw_index.argtypes = [C.c_int, C.c_uint32]
+    lib.ref_e4k_if_bw_hz.argtypes = [C.c_int, C.c_int]
+    lib.ref_e4k_if_bw_hz.restype = C.c_uint32
+    rng = np.random.default_rng(4)
+    freqs = [0, 1, 0xFFFFFFFF, 360000000, 370000000, 369999999, 370000001, 1310000000, 1750000000]
+    freqs += [int(v) for v in rng.integers(50_000_000, 2_200_000_000, 3000)]
+    # every midpoint between neighbouring centres, +-1 Hz (where the choice flips)
+    centres = [360, 380, 405, 425, 450, 475, 505, 540, 575, 615, 670, 720, 760, 840, 890, 970,
+               1300, 1320, 1360, 1410, 1445, 1460, 1490, 1530, 1560, 1590, 1640, 1660, 1680, 1700, 1720, 1750]
+    for lo, hi in zip(centres, centres[1:]):
+        mid = (lo + hi) * 500000
+        freqs += [mid - 1, mid, mid + 1]
+    for band in (0, 1, 2, 3, 4):
+        for f in freqs:
+            assert b.e4k_rf_filter(band, f) == lib.ref_e4k_rf_filter(band, f), (band, f)
+    bws = [0, 1, 999999, 1000000, 2400000, 27000000, 0xFFFFFFFF] + list(range(900000, 28000000, 12500))
+    for filt in (0, 1, 2, 3):
+        for bw in bws:
+            idx = lib.ref_e4k_if_bw_index(filt, bw)
+            want_hz = lib.ref_e4k_if_bw_hz(filt, idx) if filt < 3 else 0
+            assert b.e4k_if_bw_index(filt, bw) == (idx, want_hz), (filt, bw)
+    # the CLI agrees with the library (the path the other front-end tests use)
+    assert ref("--e4k-rf", 2, 433920000) == ["3"]
+    assert ref("--e4k-ifbw", 1, 2400000) == ["26", "2400000"]
