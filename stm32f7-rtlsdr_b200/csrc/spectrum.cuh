@@ -45,6 +45,14 @@
 #ifndef B200_SPEC_MERGE_TW
 #define B200_SPEC_MERGE_TW 1 /* fold the inter-pass twiddles into the first butterfly stage of pass 2 */
 #endif
+#ifndef B200_SPEC_REUSE
+#define B200_SPEC_REUSE 0 /* keep the upper 16 sample words of frame m in registers as the lower 16 of frame m+1 */
+#endif
+/* TIMING EXPERIMENTS ONLY (results are wrong when non-zero; tools/gpu_variants.sh): bit 0 no window
+ * loads, bit 1 no twiddle loads, bit 2 no transpose, bit 3 no global loads */
+#ifndef B200_SPEC_EXPERIMENT
+#define B200_SPEC_EXPERIMENT 0
+#endif
 #define B200_SPEC_WARPS 4
 #define B200_SPEC_THREADS (32 * B200_SPEC_WARPS)
 #define B200_SPEC_XP 33 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free */
@@ -60,6 +68,12 @@
 #define B200_DYN_SMEM(name) unsigned char *name = EMU_DYN_SMEM
 #else
 #define B200_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+#if B200_SPEC_EXPERIMENT & 8
+#define B200_SPEC_LOAD(ptr) ((uint32_t)(uintptr_t)(ptr) * 2654435761u >> 16)
+#else
+#define B200_SPEC_LOAD(ptr) ((uint32_t)__ldg(ptr))
 #endif
 
 struct SpectrumParams {
@@ -117,6 +131,9 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 
     const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
     const float *my_win = s_win + lane * B200_SPEC_WP;
+#if B200_SPEC_EXPERIMENT & 3
+    const float fake_w = my_win[0] + 0.5f;
+#endif
 
     /* software pipeline: the 32 two-byte loads of frame m+1 are issued before the FFT of frame m,
      * so no warp ever waits on HBM/L2 latency with only three warps per scheduler resident */
@@ -124,19 +141,23 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
     uint32_t raw[32];
     if (B200_SPEC_PREFETCH && m_begin < m_end) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m_begin * 512u + 32 * j);
+        for (int j = 0; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src0 + (uint64_t)m_begin * 512u + 32 * j);
     }
     for (uint32_t m = m_begin; m < m_end; ++m) {
         c2 v[32];
         if (!B200_SPEC_PREFETCH) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m * 512u + 32 * j);
+            for (int j = 0; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src0 + (uint64_t)m * 512u + 32 * j);
         }
         /* convert, window and first DIT stage of pass 1 in one go: butterfly i takes samples
          * e = bitrev5(2 i) and e + 16:  X = a wa + b wb,  Y = a wa - b wb  (3 packed ops) */
 #pragma unroll
         for (int i2 = 0; i2 < 8; ++i2) {
+#if B200_SPEC_EXPERIMENT & 1
+            const float4 w4 = make_float4(fake_w, fake_w, fake_w, fake_w);
+#else
             const float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * i2);
+#endif
             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii) {
@@ -155,8 +176,16 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         }
         if (B200_SPEC_PREFETCH && m + 1 < m_end) {
             const unsigned short *src = src0 + (uint64_t)(m + 1) * 512u;
+#if B200_SPEC_REUSE
+            /* samples t + 32 (j + 16) of frame m are samples t + 32 j of frame m + 1 (hop 512) */
 #pragma unroll
-            for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src + 32 * j);
+            for (int j = 0; j < 16; ++j) raw[j] = raw[j + 16];
+#pragma unroll
+            for (int j = 16; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src + 32 * j);
+#else
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src + 32 * j);
+#endif
         }
         b200_stage_k<4, 0>::run(v);
         b200_stage_k<8, 0>::run(v);
@@ -173,12 +202,14 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         /* transpose through the warp-private tile: row = k1 (the reader's lane), column = source lane t.
          * The barrier that keeps this frame's stores behind the previous frame's loads sits HERE, a whole
          * pass later than those loads, so it never waits on them. */
+#if !(B200_SPEC_EXPERIMENT & 4)
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) s_xp[k1 * B200_SPEC_XP + lane] = v[k1];
         __syncwarp();
 #pragma unroll
         for (int t = 0; t < 32; ++t) v[b200_bitrev5(t)] = s_xp[lane * B200_SPEC_XP + t];
+#endif
 #if B200_SPEC_MERGE_TW
         /* first DIT stage of pass 2 with the four-step twiddles folded in: slots (2i, 2i+1) hold the
          * elements e = bitrev5(2i) < 16 and e + 16 of this lane's column; X = Ta a + Tb b, Y = Ta a - Tb b
@@ -186,7 +217,11 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = b200_bitrev5(2 * i);
+#if B200_SPEC_EXPERIMENT & 2
+            const float4 tw = make_float4(fake_w, fake_w, fake_w, fake_w);
+#else
             const float4 tw = *reinterpret_cast<const float4 *>(s_tw + (e * 32 + lane) * 2);
+#endif
             const c2 pa = (e == 0) ? v[2 * i] : c2_cmul(v[2 * i], tw.x, tw.y);
             const c2 x = c2_cfma(v[2 * i + 1], tw.z, tw.w, pa);
             v[2 * i + 1] = c2_two_a_minus(pa, x);

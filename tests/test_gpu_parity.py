@@ -110,6 +110,29 @@ def test_spectrum_batches(sdr, g, n_captures, len_each):
         spec_check(out[c], gold) if frames >= 200 else spec_check_few_frames(out[c], gold)
 
 
+
+def test_spectrum_cufft_cross_check(sdr, g):
+    """north_star: "cuFFT is used only as a cross-check, never on the product path".  A full 10 s
+    capture through torch.fft (cuFFT Z2Z, float64), against the product spectrum AND the golden
+    model -- three independent FFT implementations agreeing."""
+    torch = pytest.importorskip("torch")
+    len_each = 48_000_000
+    iq = g.synth(1, len_each, SYNTH_MULTITONE, 77)
+    out = sdr.spectrum(iq)[0].astype(np.float64)
+    w = torch.from_numpy(0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(1024) / 1024.0)).cuda()
+    assert np.max(np.abs(sdr.get_window(WIN_HANN) - w.cpu().numpy())) <= 6e-8  # the table the kernel uses
+    x = torch.from_numpy(iq.reshape(-1, 2)).cuda().to(torch.float64) - 127.5
+    frames = torch.complex(x[:, 0], x[:, 1]).unfold(0, 1024, 512)
+    assert frames.shape[0] == 46874
+    acc = torch.zeros(1024, dtype=torch.float64, device="cuda")
+    for lo in range(0, frames.shape[0], 8192):  # bounded temporaries
+        acc += (torch.fft.fft(frames[lo:lo + 8192] * w, dim=1).abs() ** 2).sum(0)
+    cufft = (acc / frames.shape[0]).cpu().numpy()
+    spec_check(out, cufft)
+    gold, _ = g.spectrum(iq)
+    assert np.max(np.abs(gold - cufft) / cufft) <= 1e-9  # float64 golden vs float64 cuFFT
+
+
 def test_spectrum_short_capture_is_zero(sdr):
     assert not sdr.spectrum(np.zeros(2032, np.uint8)).any()  # < 1024 samples: no frame
 

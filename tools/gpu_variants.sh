@@ -1,10 +1,13 @@
 #!/bin/bash
-# build several compile-time variants ON the box and bench each (spectrum / wbfm chain numbers)
+# bench the prebuilt compile-time variants (tools/build_variants.sh) one after the other on the box:
+# each build/variants/<n>.so is put in the library's place, bench.py runs, the original is restored.
 mkdir -p gpurun_out
 : > gpurun_out/variants.txt
-while IFS= read -r v; do
-  [ -z "$v" ] && continue
-  B200_NVCC_EXTRA="$v" python stm32f7-rtlsdr_b200/build.py --force > /dev/null 2>&1 || { echo "BUILD FAILED: $v" >> gpurun_out/variants.txt; continue; }
+LIB=stm32f7-rtlsdr_b200/libb200sdr.so
+cp $LIB build/variants/original.so
+for so in $(ls build/variants/[0-9]*.so | sort -V); do
+  v=$(cat ${so%.so}.flags)
+  cp $so $LIB
   timeout 600 python bench.py --steps 3 --warmup 3 --captures-per-gpu 96 --e2e-captures 4 --no-cpu-baseline > gpurun_out/bench_var.txt 2>&1
   python - "$v" <<'PY' >> gpurun_out/variants.txt
 import json, sys
@@ -15,5 +18,6 @@ try:
 except Exception as e:
     print(sys.argv[1], 'FAILED', e, open('gpurun_out/bench_var.txt').read()[-500:])
 PY
-done < tools/variants.list
+done
+cp build/variants/original.so $LIB
 cat gpurun_out/variants.txt
