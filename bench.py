@@ -335,6 +335,20 @@ def main():
         ingest = {"api": "process_samples", "block_bytes": blk, "blocks": n_blocks, "MSps": n_blocks * blk / 2 / dt / 1e6,
                   "us_per_block": dt / n_blocks * 1e6, "busy_returns": busy, "realtime_factor_at_2.4MSps": n_blocks * blk / 2 / dt / 2.4e6}
         s2.close()
+        # the firmware's own cadence from a plain C caller (examples/firmware_cadence.c): ONE 512-byte
+        # buffer re-armed after every process_samples() call, spectrum read back every 4096 blocks
+        fw = os.path.join(ROOT, "build", "firmware_cadence")
+        if os.path.exists(fw):
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+            for key, argv in (("firmware_512B_coalesced", ["96000000", "512", "0", "262144", "4096"]),
+                              ("firmware_512B_per_block", ["2048000", "512", "4", "262144", "4096"])):
+                try:
+                    out = subprocess.run([fw] + argv, capture_output=True, text=True, timeout=120, env=env).stdout
+                    kv = dict(t.split("=") for t in out.split() if "=" in t)
+                    ingest[key] = {"MSps": float(kv["MSps"]), "us_per_block": float(kv["us_per_block"]),
+                                   "realtime_factor_at_2.4MSps": float(kv["realtime"]), "blocks": int(kv["blocks"])}
+                except Exception as e:  # the probe is informative only
+                    ingest[key] = {"error": str(e)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -92,7 +92,12 @@ typedef struct b200sdr_config {
                                Reference live value 512 (usbh_rtlsdr.c:230); BASELINE block
                                262144 = DEFAULT_BUF_LENGTH (usbh_rtlsdr.h:277-278).            */
     uint32_t audio_capacity;/* streaming audio FIFO capacity in float samples per chain       */
-    uint32_t reserved[7];
+    uint32_t submit_bytes;  /* process_samples() appends blocks to the open pinned slot and
+                               submits it (one H2D + one pass of the chains) once this many
+                               bytes are pending or the next block would not fit; 0 = slot_bytes.
+                               The firmware's 512-byte URBs (usbh_rtlsdr.c:230) then cost one
+                               memcpy each; 4 submits every block on its own.                 */
+    uint32_t reserved[6];
 } b200sdr_config;
 
 /* Fill *cfg with defaults: device 0, all chains, Hann, mean, 8 slots of 262144 bytes. */
@@ -110,12 +115,15 @@ B200SDR_API int32_t b200sdr_destroy(b200sdr_ctx *ctx);
  *   iq  : host pointer, u8 interleaved I,Q (owned by the caller)
  *   len : bytes; must be a multiple of 4 and <= cfg.slot_bytes
  *   ctx : the b200sdr_ctx* (void* so the firmware-side prototype needs no extra header)
- * The block is copied into the next pinned ring slot (so the caller may reuse `iq` on
- * return, like the reference re-arms the same buffer at once), then an async H2D copy on the
- * copy stream and the enabled chains on the compute stream are enqueued.  Filter history,
- * FFT overlap, discriminator / IIR state are carried in ctx from call to call, so a stream
- * cut into blocks at any 4-byte boundaries yields exactly the result of one long block.
- * Returns B200SDR_BUSY when every ring slot is still in flight (call again).
+ * The block is appended to the open pinned ring slot (so the caller may reuse `iq` on return,
+ * like the reference re-arms the same buffer at once); once cfg.submit_bytes are pending (or the
+ * next block would not fit) the slot is submitted: an async H2D copy on the copy stream and the
+ * enabled chains on the compute stream are enqueued.  b200sdr_sync / get_spectrum / get_audio /
+ * ring_acquire submit whatever is pending first, so results always cover every accepted block.
+ * Filter history, FFT overlap, discriminator / IIR state are carried in ctx from call to call,
+ * so a stream cut into blocks at any 4-byte boundaries yields exactly the result of one long
+ * block.  Returns B200SDR_BUSY when every ring slot is still in flight (call again; nothing of
+ * the block has been taken).
  * ------------------------------------------------------------------------------------------ */
 B200SDR_API int32_t process_samples(const uint8_t *iq, uint32_t len, void *ctx);
 

@@ -38,7 +38,8 @@ class Config(C.Structure):
         ("ring_slots", C.c_uint32),
         ("slot_bytes", C.c_uint32),
         ("audio_capacity", C.c_uint32),
-        ("reserved", C.c_uint32 * 7),
+        ("submit_bytes", C.c_uint32),
+        ("reserved", C.c_uint32 * 6),
     ]
 
 
@@ -210,12 +211,14 @@ class B200Sdr:
     """One context = one GPU, like one USBH host handle = one dongle in the reference."""
 
     def __init__(self, device=0, chains=CHAIN_SPECTRUM | CHAIN_WBFM | CHAIN_AM, window=WINDOW_HANN,
-                 avg_mode=AVG_MEAN, ema_beta=0.1, ring_slots=8, slot_bytes=262144, audio_capacity=1 << 20):
+                 avg_mode=AVG_MEAN, ema_beta=0.1, ring_slots=8, slot_bytes=262144, audio_capacity=1 << 20,
+                 submit_bytes=0):
         self.lib = load_library()
         cfg = Config()
         self.lib.b200sdr_default_config(C.byref(cfg))
         cfg.device, cfg.chains, cfg.window, cfg.avg_mode = device, chains, window, avg_mode
         cfg.ema_beta, cfg.ring_slots, cfg.slot_bytes, cfg.audio_capacity = ema_beta, ring_slots, slot_bytes, audio_capacity
+        cfg.submit_bytes = submit_bytes
         self.cfg = cfg
         self.ctx = C.c_void_p()
         rc = self.lib.b200sdr_create(C.byref(cfg), C.byref(self.ctx))

@@ -71,8 +71,10 @@ struct b200sdr_ctx {
     std::vector<uint8_t> slot_used;
     uint32_t ring_head = 0;
     bool slot_acquired = false;
-    uint64_t bytes_in = 0, blocks_in = 0, busy_returns = 0;
-    uint32_t last_len = 0, last_slot = 0;
+    uint32_t pending = 0;               /* bytes appended to slot ring_head, not yet submitted      */
+    uint32_t submit_bytes = 0;          /* submit the open slot once this many bytes are pending    */
+    uint64_t bytes_in = 0, blocks_in = 0, busy_returns = 0, submits = 0;
+    uint32_t last_len = 0, last_off = 0, last_slot = 0;
 
     /* streaming: spectrum */
     uint8_t *d_spec_buf = nullptr;  /* [carry | block]                                              */
@@ -341,12 +343,19 @@ int commit_slot(b200sdr_ctx *ctx, uint32_t slot, uint32_t len)
     if (ctx->cfg.chains & B200SDR_CHAIN_AM) { rc = stream_am(ctx, d_slot, len); if (rc) return rc; }
     CU(cudaEventRecord(ctx->ev_consumed[slot], ctx->s_compute));
     ctx->slot_used[slot] = 1;
-    ctx->last_len = len;
     ctx->last_slot = slot;
-    ctx->bytes_in += len;
-    ctx->blocks_in += 1;
+    ctx->submits += 1;
     ctx->ring_head = (slot + 1) % ctx->cfg.ring_slots;
     return B200SDR_OK;
+}
+
+/* submit whatever process_samples has appended to the open slot (no-op when nothing is pending) */
+int flush_pending(b200sdr_ctx *ctx)
+{
+    if (ctx->pending == 0) return B200SDR_OK;
+    const uint32_t n = ctx->pending;
+    ctx->pending = 0;
+    return commit_slot(ctx, ctx->ring_head, n);
 }
 
 /* would this block overflow an audio FIFO?  checked before anything is enqueued */
@@ -417,6 +426,7 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     if (cfg.slot_bytes < 4 || (cfg.slot_bytes & 3u)) return B200SDR_NOT_SUPPORTED; /* multiple-of-4 rule */
     if (cfg.avg_mode == B200SDR_AVG_EMA && !(cfg.ema_beta > 0.0f && cfg.ema_beta < 1.0f)) return B200SDR_NOT_SUPPORTED;
     if (cfg.audio_capacity < 4096) cfg.audio_capacity = 4096;
+    if (cfg.submit_bytes > cfg.slot_bytes) return B200SDR_NOT_SUPPORTED;
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || cfg.device < 0 || cfg.device >= n_dev)
@@ -425,6 +435,7 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     if (!ctx) return B200SDR_FAIL;
     ctx->cfg = cfg;
     ctx->device = cfg.device;
+    ctx->submit_bytes = cfg.submit_bytes ? cfg.submit_bytes : cfg.slot_bytes;
     DeviceGuard guard(ctx->device);
 #define CK(call)                                                                               \
     do {                                                                                       \
@@ -547,12 +558,26 @@ int32_t process_samples(const uint8_t *iq, uint32_t len, void *vctx)
     if ((len & 3u) || len > ctx->cfg.slot_bytes) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4 and <= slot_bytes");
     if (ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "a ring slot is acquired; commit it first");
     DeviceGuard guard(ctx->device);
-    if (!fifo_room(ctx, len)) { ctx->busy_returns++; return fail(ctx, B200SDR_BUSY, "audio FIFO full: call b200sdr_get_audio"); }
+    /* blocks are appended to the open pinned slot; the slot is submitted (one H2D + one pass of the
+     * chains) once cfg.submit_bytes are pending or the next block would not fit */
+    if (ctx->pending + len > ctx->cfg.slot_bytes) {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
+    if (!fifo_room(ctx, ctx->pending + len)) { ctx->busy_returns++; return fail(ctx, B200SDR_BUSY, "audio FIFO full: call b200sdr_get_audio"); }
     const uint32_t slot = ctx->ring_head;
-    int rc = slot_ready(ctx, slot);
-    if (rc) return rc;
-    memcpy(ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes, iq, len);
-    return commit_slot(ctx, slot, len);
+    if (ctx->pending == 0) { /* opening a slot: its previous H2D must have finished */
+        int rc = slot_ready(ctx, slot);
+        if (rc) return rc;
+    }
+    memcpy(ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes + ctx->pending, iq, len);
+    ctx->last_off = ctx->pending;
+    ctx->last_len = len;
+    ctx->pending += len;
+    ctx->bytes_in += len;
+    ctx->blocks_in += 1;
+    if (ctx->pending >= ctx->submit_bytes) return flush_pending(ctx);
+    return B200SDR_OK;
 }
 
 int32_t b200sdr_ring_acquire(b200sdr_ctx *ctx, uint8_t **slot_ptr, uint32_t *slot_bytes)
@@ -560,8 +585,10 @@ int32_t b200sdr_ring_acquire(b200sdr_ctx *ctx, uint8_t **slot_ptr, uint32_t *slo
     if (!ctx || !slot_ptr) return B200SDR_FAIL;
     if (ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "slot already acquired");
     DeviceGuard guard(ctx->device);
+    int rc = flush_pending(ctx); /* keep stream order: blocks appended by process_samples go first */
+    if (rc) return rc;
     const uint32_t slot = ctx->ring_head;
-    int rc = slot_ready(ctx, slot);
+    rc = slot_ready(ctx, slot);
     if (rc) return rc;
     *slot_ptr = ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes;
     if (slot_bytes) *slot_bytes = ctx->cfg.slot_bytes;
@@ -578,6 +605,10 @@ int32_t b200sdr_ring_commit(b200sdr_ctx *ctx, uint32_t len)
     ctx->slot_acquired = false;
     if (len == 0) return B200SDR_OK;
     DeviceGuard guard(ctx->device);
+    ctx->last_off = 0;
+    ctx->last_len = len;
+    ctx->bytes_in += len;
+    ctx->blocks_in += 1;
     return commit_slot(ctx, ctx->ring_head, len);
 }
 
@@ -585,6 +616,10 @@ int32_t b200sdr_sync(b200sdr_ctx *ctx)
 {
     if (!ctx) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
+    if (!ctx->slot_acquired) {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->s_copy));
     CU(cudaStreamSynchronize(ctx->s_compute));
     return B200SDR_OK;
@@ -594,6 +629,7 @@ int32_t b200sdr_reset(b200sdr_ctx *ctx)
 {
     if (!ctx) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
+    ctx->pending = 0; /* blocks not yet submitted belong to the capture being forgotten */
     int rc = b200sdr_sync(ctx);
     if (rc) return rc;
     return reset_stream_state(ctx);
@@ -603,6 +639,10 @@ int32_t b200sdr_get_spectrum(b200sdr_ctx *ctx, float *out1024, uint64_t *n_frame
 {
     if (!ctx || !out1024) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
+    if (!ctx->slot_acquired) {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->s_compute));
     CU(cudaMemcpy(out1024, ctx->d_spec_acc, 1024 * sizeof(float), cudaMemcpyDeviceToHost));
     if (ctx->cfg.avg_mode == B200SDR_AVG_MEAN && ctx->spec_frames) {
@@ -617,6 +657,10 @@ int32_t b200sdr_get_audio(b200sdr_ctx *ctx, uint32_t chain, float *out, uint32_t
 {
     if (!ctx || !out) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
+    if (!ctx->slot_acquired) {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     if (chain == B200SDR_CHAIN_WBFM) return pop_fifo(ctx, ctx->fm_fifo, out, capacity, n_out);
     if (chain == B200SDR_CHAIN_AM) return pop_fifo(ctx, ctx->am_fifo, out, capacity, n_out);
     return fail(ctx, B200SDR_NOT_SUPPORTED, "chain has no audio output");
@@ -635,10 +679,14 @@ int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capaci
 {
     if (!ctx || !out) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
+    if (!ctx->slot_acquired) {
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->s_copy));
     CU(cudaStreamSynchronize(ctx->s_compute));
     uint32_t n = ctx->last_len < capacity ? ctx->last_len : capacity;
-    if (n) CU(cudaMemcpy(out, ctx->d_ring + (size_t)ctx->last_slot * ctx->cfg.slot_bytes, n, cudaMemcpyDeviceToHost));
+    if (n) CU(cudaMemcpy(out, ctx->d_ring + (size_t)ctx->last_slot * ctx->cfg.slot_bytes + ctx->last_off, n, cudaMemcpyDeviceToHost));
     if (len) *len = ctx->last_len;
     return B200SDR_OK;
 }
@@ -846,6 +894,10 @@ int32_t b200sdr_render_spectrum(b200sdr_ctx *ctx, const float *spectrum_host, fl
 {
     if (!ctx || !argb_host) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
+    if (!spectrum_host && !ctx->slot_acquired) { /* the streaming spectrum must include every accepted block */
+        int frc = flush_pending(ctx);
+        if (frc) return frc;
+    }
     const size_t img_bytes = (size_t)B200_LCD_W * B200_LCD_H * sizeof(uint32_t);
     uint32_t *d_img = nullptr;
     float *d_spec = nullptr;

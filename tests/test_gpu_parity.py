@@ -241,14 +241,16 @@ def random_cuts(total, max_block, seed):
     return cuts
 
 
+@pytest.mark.parametrize("submit_bytes", [0, 4], ids=["coalesced", "per_block"])
 @pytest.mark.parametrize("cuts_kind", ["baseline_blocks", "reference_512", "random"])
-def test_streaming_all_chains_block_cut_invariance(sdr_lib, g, cuts_kind):
-    """A stream cut into blocks at arbitrary 4-byte boundaries gives the single-capture result."""
+def test_streaming_all_chains_block_cut_invariance(sdr_lib, g, cuts_kind, submit_bytes):
+    """A stream cut into blocks at arbitrary 4-byte boundaries gives the single-capture result,
+    whether blocks are coalesced into full ring slots (default) or submitted one by one."""
     total = 262144 * 3 + 512 * 5
     iq = g.synth(1, total, SYNTH_WBFM, 90)
     cuts = {"baseline_blocks": [262144] * 3 + [512 * 5], "reference_512": [512] * (total // 512),
             "random": random_cuts(total, 65536, 7)}[cuts_kind]
-    with sdr_lib.B200Sdr(slot_bytes=262144, ring_slots=4) as s:
+    with sdr_lib.B200Sdr(slot_bytes=262144, ring_slots=4, submit_bytes=submit_bytes) as s:
         feed(s, iq, cuts)
         spec, frames = s.get_spectrum()
         fm = s.get_audio(sdr_lib.CHAIN_WBFM)
@@ -306,6 +308,41 @@ def test_ingest_bytes_match_reference_copy(sdr_lib, g, tmp_path):
     if ref.available:
         out, _ = ref.run_stream(data, 512, 7, str(tmp_path))
         assert np.array_equal(out, data)
+
+
+def test_small_blocks_are_coalesced_into_ring_slots(sdr_lib, g):
+    """The firmware hands over 512-byte URBs (usbh_rtlsdr.c:230).  By default they are appended to the
+    open pinned slot and go to the device one full slot at a time; the getters submit what is
+    pending, so nothing is ever missing from a result, and the last block is where it should be."""
+    iq = g.synth(1, 262144 + 512 * 3, SYNTH_MULTITONE, 94)
+    launches = {}
+    for mode, submit in (("coalesced", 0), ("per_block", 4)):
+        with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM, submit_bytes=submit) as s:
+            before = s.kernel_launches()
+            feed(s, iq, [512] * (iq.size // 512))
+            got, n = s.debug_last_block(512)
+            assert n == 512 and np.array_equal(got, iq[-512:])
+            spec, frames = s.get_spectrum()
+            launches[mode] = s.kernel_launches() - before
+            assert s.counters()["blocks_in"] == iq.size // 512 and s.counters()["bytes_in"] == iq.size
+        assert frames == (iq.size - 2048) // 1024 + 1
+        spec_check(spec, g.spectrum(iq)[0])
+    assert launches["coalesced"] <= 4 and launches["per_block"] >= 500
+    with pytest.raises(sdr_lib.B200SdrError) as ei:
+        sdr_lib.B200Sdr(slot_bytes=4096, submit_bytes=8192)
+    assert ei.value.status == sdr_lib.NOT_SUPPORTED
+
+
+def test_ring_acquire_after_pending_blocks_keeps_stream_order(sdr_lib, g):
+    iq = g.synth(1, 262144 + 4096, SYNTH_MULTITONE, 95)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        s.process_samples(iq[:4096])           # stays pending in the open slot
+        slot = s.ring_acquire()                # must submit the pending bytes first
+        slot[:] = iq[4096:]
+        s.ring_commit(262144)
+        spec, frames = s.get_spectrum()
+    assert frames == (iq.size - 2048) // 1024 + 1
+    spec_check(spec, g.spectrum(iq)[0])
 
 
 def test_ring_acquire_commit_zero_copy(sdr_lib, g):
@@ -424,13 +461,14 @@ def test_many_small_captures(sdr, g):
         assert np.max(np.abs(am[c] - g.am(blk))) <= AM_AUDIO_ATOL
 
 
-def test_streaming_tiny_blocks(sdr_lib, g):
+@pytest.mark.parametrize("submit_bytes", [0, 4, 64], ids=["coalesced", "per_block", "every_64B"])
+def test_streaming_tiny_blocks(sdr_lib, g, submit_bytes):
     """Blocks far smaller than a frame or a FIR chunk (down to the 4-byte minimum)."""
     total = 4 * 1500
     iq = g.synth(1, total, SYNTH_WBFM, 77)
     cuts = [4] * 300 + [8] * 100 + [12] * 50 + [4000 - 0]
     cuts = cuts[:-1] + [total - sum(cuts[:-1])]
-    with sdr_lib.B200Sdr(slot_bytes=4096, ring_slots=3) as s:
+    with sdr_lib.B200Sdr(slot_bytes=4096, ring_slots=3, submit_bytes=submit_bytes) as s:
         feed(s, iq, cuts)
         spec, frames = s.get_spectrum()
         fm = s.get_audio(sdr_lib.CHAIN_WBFM)
