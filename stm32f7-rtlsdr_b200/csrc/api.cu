@@ -32,9 +32,10 @@ constexpr uint32_t kAmLeftMax = 400;         /* < one 200-sample chunk          
 constexpr uint64_t kWaveBytesDefault = 192ull << 20;
 
 struct AudioFifo {
-    float *d_buf = nullptr;   /* device FIFO storage (linear, compacted on pop)                    */
+    float *d_buf = nullptr;   /* device FIFO storage: valid floats are d_buf[head .. head + count)  */
+    float *d_spare = nullptr; /* same size; compaction copies into it and swaps (no overlapping)   */
     uint32_t capacity = 0;    /* floats                                                            */
-    uint32_t count = 0;       /* valid floats starting at d_buf[0]                                 */
+    uint32_t head = 0, count = 0;
 };
 
 } // namespace
@@ -210,6 +211,7 @@ int launch_am_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
 }
 
 bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where);
 
 /* ---- streaming steps (all on the compute stream, after the block is in d_ring[slot]) ---- */
 int stream_spectrum(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
@@ -249,8 +251,8 @@ int stream_wbfm(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     p.tiles_per_segment = p.n_tiles;
     const uint64_t a0 = b200::ceil_div(p.m_base, B200_FM_D2), a1 = b200::ceil_div(p.m_base + p.m1, B200_FM_D2);
     const uint32_t n_audio = (uint32_t)(a1 - a0);
-    if (ctx->fm_fifo.count + n_audio > ctx->fm_fifo.capacity) return fail(ctx, B200SDR_FAIL, "WBFM audio FIFO overflow");
-    p.audio = ctx->fm_fifo.d_buf + ctx->fm_fifo.count;
+    int frc = fifo_reserve(ctx, ctx->fm_fifo, n_audio, &p.audio);
+    if (frc) return frc;
     p.audio_base = a0;
     p.state = ctx->d_fm_state;
     k_wbfm<<<dim3(1, 1), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_compute>>>(p);
@@ -273,7 +275,9 @@ int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     if (n_chunks == 0) { ctx->am_left = have; return B200SDR_OK; }
     const uint64_t a0 = (2 * ctx->am_chunks + 2) / 3, a1 = (2 * (ctx->am_chunks + n_chunks) + 2) / 3;
     const uint32_t n_audio = (uint32_t)(a1 - a0);
-    if (ctx->am_fifo.count + n_audio > ctx->am_fifo.capacity) return fail(ctx, B200SDR_FAIL, "AM audio FIFO overflow");
+    float *am_out = nullptr;
+    int frc = fifo_reserve(ctx, ctx->am_fifo, n_audio, &am_out);
+    if (frc) return frc;
     AmFrontParams p{};
     p.iq = ctx->d_am_buf;
     p.capture_bytes = (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
@@ -289,7 +293,7 @@ int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     b.env = ctx->d_am_env_stream;
     b.q_count = n_chunks;
     b.q_base = ctx->am_chunks;
-    b.audio = ctx->am_fifo.d_buf + ctx->am_fifo.count;
+    b.audio = am_out;
     b.audio_base = a0;
     b.state = ctx->d_amb_state;
     k_am_back<<<1, B200_AMB_THREADS, 0, ctx->s_compute>>>(b);
@@ -307,8 +311,8 @@ int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
 int reset_stream_state(b200sdr_ctx *ctx)
 {
     ctx->spec_have = 0; ctx->spec_frames = 0;
-    ctx->fm_left = 0; ctx->fm_chunks = 0; ctx->fm_fifo.count = 0;
-    ctx->am_left = 0; ctx->am_chunks = 0; ctx->am_fifo.count = 0;
+    ctx->fm_left = 0; ctx->fm_chunks = 0; ctx->fm_fifo.count = 0; ctx->fm_fifo.head = 0;
+    ctx->am_left = 0; ctx->am_chunks = 0; ctx->am_fifo.count = 0; ctx->am_fifo.head = 0;
     CU(cudaMemsetAsync(ctx->d_spec_acc, 0, 1024 * sizeof(float), ctx->s_compute));
     CU(cudaMemsetAsync(ctx->d_fm_state, 0, sizeof(FmState), ctx->s_compute));
     CU(cudaMemsetAsync(ctx->d_amf_state, 0, sizeof(AmFrontState), ctx->s_compute));
@@ -376,19 +380,26 @@ int slot_ready(b200sdr_ctx *ctx, uint32_t slot)
     return fail(ctx, B200SDR_FAIL, "cudaEventQuery", q);
 }
 
+/* contiguous room for n more floats behind the queued ones (compacting if the tail is used up) */
+int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where)
+{
+    if (f.count + n > f.capacity) return fail(ctx, B200SDR_FAIL, "audio FIFO overflow");
+    if (f.head + f.count + n > f.capacity) {
+        CU(cudaMemcpyAsync(f.d_spare, f.d_buf + f.head, (size_t)f.count * sizeof(float), cudaMemcpyDeviceToDevice, ctx->s_compute));
+        float *t = f.d_buf; f.d_buf = f.d_spare; f.d_spare = t;
+        f.head = 0;
+    }
+    *where = f.d_buf + f.head + f.count;
+    return B200SDR_OK;
+}
+
 int pop_fifo(b200sdr_ctx *ctx, AudioFifo &f, float *out, uint32_t capacity, uint32_t *n_out)
 {
     CU(cudaStreamSynchronize(ctx->s_compute));
-    uint32_t n = f.count < capacity ? f.count : capacity;
-    if (n) CU(cudaMemcpy(out, f.d_buf, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    const uint32_t rest = f.count - n;
-    if (rest && n) {
-        /* compact through the bounce buffer in pieces (rare: caller's buffer was too small) */
-        std::vector<float> tmp(rest);
-        CU(cudaMemcpy(tmp.data(), f.d_buf + n, (size_t)rest * sizeof(float), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(f.d_buf, tmp.data(), (size_t)rest * sizeof(float), cudaMemcpyHostToDevice));
-    }
-    f.count = rest;
+    const uint32_t n = f.count < capacity ? f.count : capacity;
+    if (n) CU(cudaMemcpy(out, f.d_buf + f.head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    f.count -= n;
+    f.head = f.count ? f.head + n : 0;
     if (n_out) *n_out = n;
     return B200SDR_OK;
 }
@@ -446,6 +457,7 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
             return B200SDR_FAIL;                                                               \
         }                                                                                      \
     } while (0)
+    try { /* std::vector growth below may throw; nothing may unwind through the C boundary */
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, ctx->device));
     if (prop.major < 10) {
@@ -515,8 +527,15 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     ctx->am_fifo.capacity = cfg.audio_capacity;
     CK(cudaMalloc((void **)&ctx->fm_fifo.d_buf, (size_t)cfg.audio_capacity * sizeof(float)));
     CK(cudaMalloc((void **)&ctx->am_fifo.d_buf, (size_t)cfg.audio_capacity * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->fm_fifo.d_spare, (size_t)cfg.audio_capacity * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->am_fifo.d_spare, (size_t)cfg.audio_capacity * sizeof(float)));
     if (reset_stream_state(ctx) != B200SDR_OK) { b200sdr_destroy(ctx); return B200SDR_FAIL; }
     CK(cudaStreamSynchronize(ctx->s_compute));
+    } catch (...) {
+        fprintf(stderr, "b200sdr_create: out of host memory\n");
+        b200sdr_destroy(ctx);
+        return B200SDR_FAIL;
+    }
 #undef CK
     *out_ctx = ctx;
     return B200SDR_OK;
@@ -539,7 +558,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     void *dev_ptrs[] = {ctx->d_ring, ctx->d_spec_buf, ctx->d_bounce, ctx->d_spec_acc, ctx->d_fm_buf, ctx->d_am_buf,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
-                        ctx->am_fifo.d_buf, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
+                        ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
                         ctx->d_res_am};
     for (void *p : dev_ptrs) if (p) cudaFree(p);

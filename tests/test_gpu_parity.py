@@ -333,6 +333,39 @@ def test_small_blocks_are_coalesced_into_ring_slots(sdr_lib, g):
     assert ei.value.status == sdr_lib.NOT_SUPPORTED
 
 
+def test_audio_fifo_partial_pops_and_back_pressure(sdr_lib, g):
+    """A small audio FIFO drained in odd-sized pieces: BUSY when a block's audio would not fit, nothing
+    lost or reordered across partial pops and the FIFO's internal compaction."""
+    total = 65536 * 24
+    iq = g.synth(1, total, SYNTH_WBFM, 96)
+    got_fm, got_am, pos, busy = [], [], 0, 0
+    rng = np.random.default_rng(5)
+    with sdr_lib.B200Sdr(slot_bytes=65536, ring_slots=3, audio_capacity=4096, submit_bytes=4,
+                         chains=sdr_lib.CHAIN_WBFM | sdr_lib.CHAIN_AM) as s:
+        while pos < total:
+            rc = s.process_samples(iq[pos:pos + 65536], allow_busy=True)
+            if rc == 1:
+                busy += 1
+                got_fm.append(s.get_audio(sdr_lib.CHAIN_WBFM, int(rng.integers(1, 1500))))
+                got_am.append(s.get_audio(sdr_lib.CHAIN_AM, int(rng.integers(1, 300))))
+                continue
+            pos += 65536
+            if rng.integers(0, 3) == 0:
+                got_fm.append(s.get_audio(sdr_lib.CHAIN_WBFM, int(rng.integers(1, 700))))
+        while True:
+            a, b = s.get_audio(sdr_lib.CHAIN_WBFM, 333), s.get_audio(sdr_lib.CHAIN_AM, 77)
+            got_fm.append(a)
+            got_am.append(b)
+            if a.size == 0 and b.size == 0:
+                break
+    fm, am = np.concatenate(got_fm), np.concatenate(got_am)
+    assert busy > 0
+    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_am = (2 * (total // 2 // 200) + 2) // 3
+    assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
+    assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
+
+
 def test_ring_acquire_after_pending_blocks_keeps_stream_order(sdr_lib, g):
     iq = g.synth(1, 262144 + 4096, SYNTH_MULTITONE, 95)
     with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
