@@ -199,6 +199,14 @@ B200SDR_API int32_t b200sdr_render_spectrum(b200sdr_ctx *ctx, const float *spect
                                             uint32_t *argb_host /* 480*272 */);
 B200SDR_API int32_t b200sdr_render_spectrum_dev(b200sdr_ctx *ctx, const float *spectra_dev, uint32_t n_spectra,
                                                 float scale, float db_min, float db_max, uint32_t *argb_dev);
+/* Waterfall (spectrogram) view on the same panel: image row r shows spectrum r of `n_rows` x 1024
+ * (e.g. the output of b200sdr_batch_spectrum_dev over consecutive slices of a capture) in the colour
+ * of the bar height that power would reach; black below db_min and for rows >= n_rows; at most the
+ * first 272 spectra are shown. */
+B200SDR_API int32_t b200sdr_render_waterfall(b200sdr_ctx *ctx, const float *spectra_host, uint32_t n_rows, float db_min,
+                                             float db_max, uint32_t *argb_host /* 480*272 */);
+B200SDR_API int32_t b200sdr_render_waterfall_dev(b200sdr_ctx *ctx, const float *spectra_dev, uint32_t n_rows,
+                                                 float scale, float db_min, float db_max, uint32_t *argb_dev);
 
 /* The FIR taps / window the device uses (float, as uploaded), for parity against the oracle. */
 B200SDR_API int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *out, uint32_t capacity,

@@ -418,6 +418,41 @@ void gold_render_spectrum(const float *power1024, double db_min, double db_max, 
     }
 }
 
+/* Waterfall (spectrogram) view of the same LCD: image row r shows spectrum r (rows >= n_rows stay
+ * black); column -> bins as in the bar plot; the colour is the ramp entry of the bar height that
+ * power would get (height 0 = below db_min = black). */
+void gold_render_waterfall(const float *spectra, uint32_t n_rows, double db_min, double db_max, uint32_t *argb)
+{
+    float thr[272];
+    gold_render_thresholds(db_min, db_max, thr);
+    for (int r = 0; r < 272; ++r) {
+        for (int c = 0; c < 480; ++c) {
+            uint32_t px = 0xFF000000u;
+            if ((uint32_t)r < n_rows) {
+                const float *power1024 = spectra + (size_t)r * 1024;
+                int s0 = (c * 1024) / 480, s1 = ((c + 1) * 1024) / 480;
+                float v = 0.0f;
+                for (int s = s0; s < s1; ++s) {
+                    float pw = power1024[(s + 512) & 1023];
+                    if (pw > v) v = pw;
+                }
+                int height = 0;
+                while (height < 272 && thr[height] <= v) height++;
+                if (height > 0) {
+                    int y = height - 1;
+                    int i = (y * 255) / 271, seg = i / 64, t = (i % 64) * 4, rr, gg, bb;
+                    if (seg == 0) { rr = 0; gg = t; bb = 255; }
+                    else if (seg == 1) { rr = 0; gg = 255; bb = 255 - t; }
+                    else if (seg == 2) { rr = t; gg = 255; bb = 0; }
+                    else { rr = 255; gg = 255 - t; bb = 0; }
+                    px |= ((uint32_t)rr << 16) | ((uint32_t)gg << 8) | (uint32_t)bb;
+                }
+            }
+            argb[r * 480 + c] = px;
+        }
+    }
+}
+
 /* ---- synthetic captures ------------------------------------------------------------------ */
 static float g_lut[B200SDR_SYNTH_LUT_SIZE + 1];
 static int g_lut_ready = 0;

@@ -81,6 +81,7 @@ void gold_am(const uint8_t *iq, size_t n, real *audio);
 /* 480 x 272 ARGB8888 bar plot of a float32 power spectrum (FFT order), dB window [db_min, db_max] */
 void gold_render_thresholds(double db_min, double db_max, float *thr272);
 void gold_render_spectrum(const float *power1024, double db_min, double db_max, uint32_t *argb);
+void gold_render_waterfall(const float *spectra, uint32_t n_rows, double db_min, double db_max, uint32_t *argb);
 
 /* synthetic captures (include/b200sdr_synth.h), n_captures x len_each bytes */
 void gold_synth_fill(uint8_t *iq, uint32_t n_captures, uint64_t len_each, uint32_t kind, uint64_t first_capture);

@@ -37,6 +37,9 @@ int main(void)
     for (int k = 0; k < 1024; ++k) power[k] = (float)spec[k];
     uint32_t *img = (uint32_t *)malloc(sizeof(uint32_t) * 480 * 272);
     gold_render_spectrum(power, 0.0, 100.0, img);
+    gold_render_waterfall(power, 1, 0.0, 100.0, img);
+    gold_render_waterfall(power, 0, 0.0, 100.0, img);
+    gold_render_spectrum(power, 0.0, 100.0, img);
     printf("SELFTEST_OK frames=%llu copied=%zu px=%08x\n", (unsigned long long)frames, w, img[271 * 480 + 240]);
     free(iq); free(cf); free(audio); free(disc); free(am); free(img);
     return 0;

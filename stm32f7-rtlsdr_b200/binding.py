@@ -410,6 +410,17 @@ class B200Sdr:
         self._check(fn(self.ctx, src, db_min, db_max, img.ctypes.data), "b200sdr_render_spectrum")
         return img
 
+    def render_waterfall(self, spectra, db_min=0.0, db_max=100.0):
+        """480 x 272 ARGB8888 spectrogram: image row r shows spectra[r] (n_rows x 1024 float32)."""
+        fn = self.lib.b200sdr_render_waterfall
+        fn.restype = C.c_int32
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
+        spectra = np.ascontiguousarray(spectra, dtype=np.float32).reshape(-1, 1024)
+        img = np.empty((272, 480), dtype=np.uint32)
+        src = spectra.ctypes.data if spectra.shape[0] else None
+        self._check(fn(self.ctx, src, spectra.shape[0], db_min, db_max, img.ctypes.data), "b200sdr_render_waterfall")
+        return img
+
     def synth_fill_dev(self, iq_dev, n_captures, len_each, kind, first_capture=0):
         self._check(self.lib.b200sdr_synth_fill_dev(self.ctx, iq_dev, n_captures, len_each, kind, first_capture), "b200sdr_synth_fill_dev")
 

@@ -380,6 +380,18 @@ int slot_ready(b200sdr_ctx *ctx, uint32_t slot)
     return fail(ctx, B200SDR_FAIL, "cudaEventQuery", q);
 }
 
+/* dB thresholds of the 272 LCD rows: T[h] = 10^((db_min + (db_max - db_min) h / 271) / 10) */
+int upload_thresholds(b200sdr_ctx *ctx, float db_min, float db_max)
+{
+    float thr[B200_LCD_H];
+    for (int h = 0; h < B200_LCD_H; ++h)
+        thr[h] = (float)pow(10.0, ((double)db_min + ((double)db_max - (double)db_min) * (double)h / (B200_LCD_H - 1.0)) / 10.0);
+    if (!ctx->d_thresholds) CU(cudaMalloc((void **)&ctx->d_thresholds, sizeof thr));
+    CU(cudaMemcpyAsync(ctx->d_thresholds, thr, sizeof thr, cudaMemcpyHostToDevice, ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_compute)); /* `thr` is a stack buffer */
+    return B200SDR_OK;
+}
+
 /* contiguous room for n more floats behind the queued ones (compacting if the tail is used up) */
 int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where)
 {
@@ -897,15 +909,54 @@ int32_t b200sdr_render_spectrum_dev(b200sdr_ctx *ctx, const float *spectra_dev, 
     if (!(db_max > db_min)) return fail(ctx, B200SDR_NOT_SUPPORTED, "db_max must exceed db_min");
     if (n_spectra == 0) return B200SDR_OK;
     DeviceGuard guard(ctx->device);
-    float thr[B200_LCD_H];
-    for (int h = 0; h < B200_LCD_H; ++h)
-        thr[h] = (float)pow(10.0, ((double)db_min + ((double)db_max - (double)db_min) * (double)h / (B200_LCD_H - 1.0)) / 10.0);
-    if (!ctx->d_thresholds) CU(cudaMalloc((void **)&ctx->d_thresholds, sizeof thr));
-    CU(cudaMemcpyAsync(ctx->d_thresholds, thr, sizeof thr, cudaMemcpyHostToDevice, ctx->s_compute));
-    CU(cudaStreamSynchronize(ctx->s_compute)); /* `thr` is a stack buffer */
+    int rc = upload_thresholds(ctx, db_min, db_max);
+    if (rc) return rc;
     k_render_spectrum<<<n_spectra, B200_LCD_W, 0, ctx->s_compute>>>(spectra_dev, scale, ctx->d_thresholds, argb_dev);
     CU(cudaGetLastError());
     ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_render_waterfall_dev(b200sdr_ctx *ctx, const float *spectra_dev, uint32_t n_rows, float scale,
+                                     float db_min, float db_max, uint32_t *argb_dev)
+{
+    if (!ctx || !argb_dev || (!spectra_dev && n_rows)) return B200SDR_FAIL;
+    if (!(db_max > db_min)) return fail(ctx, B200SDR_NOT_SUPPORTED, "db_max must exceed db_min");
+    DeviceGuard guard(ctx->device);
+    int rc = upload_thresholds(ctx, db_min, db_max);
+    if (rc) return rc;
+    if (n_rows > B200_LCD_H) n_rows = B200_LCD_H; /* the panel has 272 rows */
+    k_render_waterfall<<<B200_LCD_H, B200_LCD_W, 0, ctx->s_compute>>>(spectra_dev, n_rows, scale, ctx->d_thresholds, argb_dev);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_render_waterfall(b200sdr_ctx *ctx, const float *spectra_host, uint32_t n_rows, float db_min, float db_max,
+                                 uint32_t *argb_host)
+{
+    if (!ctx || !argb_host || (!spectra_host && n_rows)) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    if (n_rows > B200_LCD_H) n_rows = B200_LCD_H;
+    const size_t img_bytes = (size_t)B200_LCD_W * B200_LCD_H * sizeof(uint32_t);
+    const size_t spec_bytes = (size_t)(n_rows ? n_rows : 1) * 1024 * sizeof(float);
+    uint32_t *d_img = nullptr;
+    float *d_spec = nullptr;
+    CU(cudaMalloc((void **)&d_img, img_bytes));
+    int rc = B200SDR_OK;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaMalloc((void **)&d_spec, spec_bytes)) != cudaSuccess) break;
+        if (n_rows && (e = cudaMemcpyAsync(d_spec, spectra_host, spec_bytes, cudaMemcpyHostToDevice, ctx->s_compute)) != cudaSuccess) break;
+        rc = b200sdr_render_waterfall_dev(ctx, d_spec, n_rows, 1.0f, db_min, db_max, d_img);
+        if (rc) break;
+        if ((e = cudaMemcpyAsync(argb_host, d_img, img_bytes, cudaMemcpyDeviceToHost, ctx->s_compute)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(ctx->s_compute);
+    } while (0);
+    cudaFree(d_img);
+    if (d_spec) cudaFree(d_spec);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "render waterfall", e);
     return B200SDR_OK;
 }
 

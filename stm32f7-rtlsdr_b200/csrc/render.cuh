@@ -70,4 +70,34 @@ __global__ void __launch_bounds__(B200_LCD_W) k_render_spectrum(const float *__r
     }
 }
 
+/* Waterfall view (oracle/golden.c gold_render_waterfall): one CTA per image row, one thread per pixel;
+ * row r shows spectrum r in the colour of the bar height its power would reach, rows >= n_rows are black. */
+__global__ void __launch_bounds__(B200_LCD_W) k_render_waterfall(const float *__restrict__ spectra, uint32_t n_rows,
+                                                               float scale, const float *__restrict__ thresholds,
+                                                               uint32_t *__restrict__ argb)
+{
+    __shared__ float s_thr[B200_LCD_H];
+    const int c = (int)threadIdx.x, r = (int)blockIdx.x;
+    if (c < B200_LCD_H) s_thr[c] = thresholds[c];
+    __syncthreads();
+    uint32_t px = 0xFF000000u;
+    if ((uint32_t)r < n_rows) {
+        const float *spec = spectra + (uint64_t)r * 1024u;
+        const int s0 = (c * 1024) / B200_LCD_W, s1 = ((c + 1) * 1024) / B200_LCD_W;
+        float v = 0.0f;
+        for (int s = s0; s < s1; ++s) {
+            const float pwr = spec[(s + 512) & 1023] * scale;
+            v = pwr > v ? pwr : v;
+        }
+        int lo = 0, hi = B200_LCD_H;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_thr[mid] <= v) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo > 0) px = b200_ramp_argb(lo - 1);
+    }
+    argb[r * B200_LCD_W + c] = px;
+}
+
 #endif

@@ -58,3 +58,55 @@ def test_render_bit_exact_against_golden(sdr_lib):
         assert np.array_equal(s.render_spectrum(rnd, 10.0, 80.0), gold_render(g, rnd, 10.0, 80.0))
         with pytest.raises(sdr_lib.B200SdrError):
             s.render_spectrum(rnd, 50.0, 50.0)
+
+
+# ---- waterfall (spectrogram) view ----------------------------------------------------------------
+def gold_waterfall(g, spectra, db_min, db_max):
+    g.lib.gold_render_waterfall.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_void_p]
+    p = np.ascontiguousarray(spectra, np.float32).reshape(-1, 1024)
+    img = np.zeros((272, 480), np.uint32)
+    g.lib.gold_render_waterfall(p.ctypes.data if p.shape[0] else None, p.shape[0], db_min, db_max, img.ctypes.data)
+    return img
+
+
+def test_golden_waterfall_rows_and_colours():
+    g = Golden()
+    spectra = np.full((3, 1024), 0.5, np.float32)   # below db_min = 0 dB: black
+    spectra[0, 0] = 1e10                            # row 0: DC at 100 dB -> centre column, top of the ramp
+    spectra[1, 512] = 1e5                           # row 1: -fs/2 at 50 dB -> column 0, mid ramp
+    spectra[2, 256] = 1.0                           # row 2: +fs/4 at exactly db_min -> bottom of the ramp
+    img = gold_waterfall(g, spectra, 0.0, 100.0)
+    bars = [gold_render(g, spectra[r], 0.0, 100.0) for r in range(3)]
+    assert np.all(img >> 24 == 0xFF)
+    assert img[0, 240] == 0xFFFF0300 and img[2, 360] == 0xFF0000FF      # red (top of ramp) / blue (bottom)
+    lit = (img & 0x00FFFFFF) != 0
+    assert lit.sum() == 3 and lit[0, 240] and lit[1, 0] and lit[2, 360]
+    # the pixel colour is the colour of the top pixel of the bar the same power draws
+    for r, c in ((0, 240), (1, 0), (2, 360)):
+        col = bars[r][:, c]
+        top = np.flatnonzero(col & 0x00FFFFFF)[0] if r != 2 else 271
+        assert img[r, c] == col[top]
+    assert np.all(img[3:] == 0xFF000000)                                 # rows >= n_rows are black
+    assert np.all(gold_waterfall(g, np.zeros((0, 1024), np.float32), 0.0, 100.0) == 0xFF000000)
+
+
+@pytest.mark.gpu
+def test_waterfall_bit_exact_against_golden(sdr_lib):
+    """A 272-row spectrogram of an FM capture: consecutive 64 KiB slices -> batch spectra -> image."""
+    g = Golden()
+    rows, slice_bytes = 272, 65536
+    iq = g.synth(1, rows * slice_bytes, 2, 5)  # SYNTH_WBFM: the carrier visibly wanders with the message
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        spectra = s.spectrum(iq, n_captures=rows)
+        assert spectra.shape == (rows, 1024)
+        for db_min, db_max in ((0.0, 100.0), (30.0, 80.0)):
+            assert np.array_equal(s.render_waterfall(spectra, db_min, db_max), gold_waterfall(g, spectra, db_min, db_max))
+        assert np.array_equal(s.render_waterfall(spectra[:100], 0.0, 100.0), gold_waterfall(g, spectra[:100], 0.0, 100.0))
+        more = np.concatenate([spectra, spectra[:30]])
+        assert np.array_equal(s.render_waterfall(more, 0.0, 100.0), gold_waterfall(g, spectra, 0.0, 100.0))  # 272 shown
+        assert np.all(s.render_waterfall(np.zeros((0, 1024), np.float32)) == 0xFF000000)
+        img = s.render_waterfall(spectra, 30.0, 80.0)
+        # the FM carrier (+50 kHz +- 75 kHz) lights columns right of centre in every row
+        assert np.all(((img[:, 240:290] & 0x00FFFFFF) != 0).any(axis=1))
+        with pytest.raises(sdr_lib.B200SdrError):
+            s.render_waterfall(spectra, 10.0, 10.0)
