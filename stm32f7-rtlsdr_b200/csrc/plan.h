@@ -36,9 +36,10 @@ inline SpectrumPlan plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint3
     SpectrumPlan pl{};
     pl.frames = (uint32_t)spectrum_frames(len_bytes);
     if (pl.frames == 0) return pl;
-    /* aim at >= 16 CTAs per SM over the whole batch, at most 256 frames per warp, at least 1 */
+    /* aim at >= 32 CTAs per SM over the whole batch (two are resident at a time: >= 16 waves, so the
+     * last partial wave costs a few percent at most), at most 256 frames per warp, at least 1 */
     const uint64_t total_frames = (uint64_t)pl.frames * n_captures;
-    const uint64_t want_warps = (uint64_t)sm_count * 16 * B200_SPEC_WARPS;
+    const uint64_t want_warps = (uint64_t)sm_count * 32 * B200_SPEC_WARPS;
     uint64_t fpw = total_frames / want_warps;
     if (fpw < 1) fpw = 1;
     if (fpw > 256) fpw = 256;

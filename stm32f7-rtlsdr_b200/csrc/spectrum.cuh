@@ -34,7 +34,7 @@
 #include "fft32.cuh"
 
 #ifndef B200_SPEC_MINB
-#define B200_SPEC_MINB 3 /* CTAs per SM the register allocation is tuned for */
+#define B200_SPEC_MINB 2 /* CTAs per SM the register allocation is tuned for (8 warps/SM, up to 255 registers) */
 #endif
 #ifndef B200_SPEC_PREFETCH
 #define B200_SPEC_PREFETCH 1 /* issue the loads of frame m+1 before the FFT of frame m */
@@ -48,6 +48,10 @@
 #ifndef B200_SPEC_REUSE
 #define B200_SPEC_REUSE 0 /* keep the upper 16 sample words of frame m in registers as the lower 16 of frame m+1 */
 #endif
+#ifndef B200_SPEC_REGCONST
+#define B200_SPEC_REGCONST 3 /* bit 0: this lane's 32 twiddles, bit 1: its 32 window values live in registers for the
+                                whole kernel instead of being re-read from shared memory every frame (needs MINB <= 2) */
+#endif
 /* TIMING EXPERIMENTS ONLY (results are wrong when non-zero; tools/gpu_variants.sh): bit 0 no window
  * loads, bit 1 no twiddle loads, bit 2 no transpose, bit 3 no global loads */
 #ifndef B200_SPEC_EXPERIMENT
@@ -55,7 +59,10 @@
 #endif
 #define B200_SPEC_WARPS 4
 #define B200_SPEC_THREADS (32 * B200_SPEC_WARPS)
-#define B200_SPEC_XP 33 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free */
+#ifndef B200_SPEC_XP
+#define B200_SPEC_XP 34 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free.
+                           34 (even): rows are 16-byte aligned and are read back with 128-bit loads, also conflict-free */
+#endif
 #define B200_SPEC_WP 36 /* window row pitch in floats */
 
 /* shared memory carve-up (bytes) */
@@ -134,6 +141,16 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #if B200_SPEC_EXPERIMENT & 3
     const float fake_w = my_win[0] + 0.5f;
 #endif
+#if B200_SPEC_REGCONST & 1
+    float4 r_tw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r_tw[i] = *reinterpret_cast<const float4 *>(s_tw + (b200_bitrev5(2 * i) * 32 + lane) * 2);
+#endif
+#if B200_SPEC_REGCONST & 2
+    float4 r_win[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r_win[i] = *reinterpret_cast<const float4 *>(my_win + 4 * i);
+#endif
 
     /* software pipeline: the 32 two-byte loads of frame m+1 are issued before the FFT of frame m,
      * so no warp ever waits on HBM/L2 latency with only three warps per scheduler resident */
@@ -155,6 +172,8 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         for (int i2 = 0; i2 < 8; ++i2) {
 #if B200_SPEC_EXPERIMENT & 1
             const float4 w4 = make_float4(fake_w, fake_w, fake_w, fake_w);
+#elif B200_SPEC_REGCONST & 2
+            const float4 w4 = r_win[i2];
 #else
             const float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * i2);
 #endif
@@ -208,7 +227,15 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         for (int k1 = 0; k1 < 32; ++k1) s_xp[k1 * B200_SPEC_XP + lane] = v[k1];
         __syncwarp();
 #pragma unroll
+#if (B200_SPEC_XP % 2) == 0 && defined(B200_PACKED_MATH)
+        for (int t = 0; t < 32; t += 2) {
+            const float4 q = *reinterpret_cast<const float4 *>(s_xp + lane * B200_SPEC_XP + t);
+            v[b200_bitrev5(t)] = c2_make(q.x, q.y);
+            v[b200_bitrev5(t + 1)] = c2_make(q.z, q.w);
+        }
+#else
         for (int t = 0; t < 32; ++t) v[b200_bitrev5(t)] = s_xp[lane * B200_SPEC_XP + t];
+#endif
 #endif
 #if B200_SPEC_MERGE_TW
         /* first DIT stage of pass 2 with the four-step twiddles folded in: slots (2i, 2i+1) hold the
@@ -219,6 +246,8 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
             const int e = b200_bitrev5(2 * i);
 #if B200_SPEC_EXPERIMENT & 2
             const float4 tw = make_float4(fake_w, fake_w, fake_w, fake_w);
+#elif B200_SPEC_REGCONST & 1
+            const float4 tw = r_tw[i];
 #else
             const float4 tw = *reinterpret_cast<const float4 *>(s_tw + (e * 32 + lane) * 2);
 #endif
