@@ -531,3 +531,19 @@ def test_example_host_driver_runs(sdr_lib, g, tmp_path):
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
     assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
     assert res.stdout.count("  bin ") == 5   # the five strongest spectrum bins are listed
+
+
+def test_example_firmware_cadence_runs(sdr_lib, tmp_path):
+    """examples/firmware_cadence.c: the firmware's one-buffer 512-byte superloop with process_samples at
+    the COMPLETE point; every block must arrive (frame count) in both submit modes."""
+    import subprocess
+    exe = tmp_path / "firmware_cadence"
+    libdir = os.path.dirname(sdr_lib.LIB_PATH)
+    subprocess.run(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "firmware_cadence.c"),
+                    "-L", libdir, "-lb200sdr", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    for total, submit in ((4_800_000, 0), (512_000, 4)):
+        res = subprocess.run([str(exe), str(total), "512", str(submit), "262144", "1000"], capture_output=True, text=True, check=True)
+        kv = dict(t.split("=") for t in res.stdout.split() if "=" in t)
+        assert res.stdout.startswith("FW_CADENCE") and int(kv["blocks"]) == total // 512
+        assert int(kv["frames"]) == (total - 2048) // 1024 + 1
+        assert float(kv["realtime"]) > 1.0   # keeps up with a 2.4 MS/s dongle
