@@ -547,3 +547,28 @@ def test_example_firmware_cadence_runs(sdr_lib, tmp_path):
         assert res.stdout.startswith("FW_CADENCE") and int(kv["blocks"]) == total // 512
         assert int(kv["frames"]) == (total - 2048) // 1024 + 1
         assert float(kv["realtime"]) > 1.0   # keeps up with a 2.4 MS/s dongle
+
+
+def test_contexts_are_independent(sdr_lib, g):
+    """Several dongles on one GPU = several contexts: blocks fed alternately, each context keeps its
+    own carried state and audio FIFO (one USBH host handle per dongle in the reference)."""
+    n_ctx, total, blk = 3, 65536 * 5 + 1000, 65536
+    streams = [g.synth(1, total, kind, 200 + i) for i, kind in enumerate((SYNTH_WBFM, SYNTH_AM, SYNTH_MULTITONE))]
+    ctxs = [sdr_lib.B200Sdr(slot_bytes=blk, ring_slots=3, submit_bytes=(0, 4, 8192)[i]) for i in range(n_ctx)]
+    try:
+        for pos in range(0, total, blk):
+            for s, iq in zip(ctxs, streams):
+                feed(s, iq[pos:pos + blk], [min(blk, total - pos)])
+        for s, iq in zip(ctxs, streams):
+            spec, frames = s.get_spectrum()
+            gold, gframes = g.spectrum(iq)
+            assert frames == gframes
+            spec_check(spec, gold)
+            fm, am = s.get_audio(sdr_lib.CHAIN_WBFM), s.get_audio(sdr_lib.CHAIN_AM)
+            n_fm = -(-((total // 2 // 120) * 12) // 5)
+            n_am = (2 * (total // 2 // 200) + 2) // 3
+            assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
+            assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
+    finally:
+        for s in ctxs:
+            s.close()
