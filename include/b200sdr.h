@@ -173,6 +173,30 @@ B200SDR_API int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const 
                                        uint32_t n_captures, uint64_t len_each, float *spectrum_host,
                                        float *wbfm_audio_host, float *am_audio_host);
 
+/* ------------------------------------------------------------------------------------------
+ * Optional exchange step: ONE long capture split in time across the
+ * GPUs of a box for latency.  Rank r (one process / one ctx per GPU) holds the slice of the
+ * capture that contains its frames (stm32f7-rtlsdr_b200/sharding.py split_capture_bytes: its
+ * frames plus the 512-sample FFT overlap) and calls b200sdr_split_spectrum_dev; ONE fused
+ * kernel reduces the local partial sums, pushes them into every peer's mailbox over NVLink
+ * peer memory, waits for all ranks and adds the contributions in rank order, so every rank
+ * ends with bitwise the same mean spectrum of the whole capture.  No library collective.
+ * Setup: every rank calls exchange_create (gets a 64-byte IPC handle of its mailbox), the
+ * handles are gathered by any means (bench/tests use torch.distributed as plumbing) and
+ * passed in rank order to exchange_connect.  Contexts living in one process use
+ * exchange_connect_local instead.  All ranks must make the same sequence of split calls.
+ * split_spectrum_dev is asynchronous on the ctx compute stream; exchange_wait blocks and
+ * returns B200SDR_FAIL if a peer did not arrive within ~5 s (the kernel's wait is bounded).
+ * Demodulators are not split this way (carried IIR state): they stay one capture per GPU.
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t b200sdr_exchange_create(b200sdr_ctx *ctx, uint32_t world, uint32_t rank, uint8_t *ipc_handle_out64);
+B200SDR_API int32_t b200sdr_exchange_connect(b200sdr_ctx *ctx, const uint8_t *ipc_handles /* world x 64 bytes */);
+B200SDR_API int32_t b200sdr_exchange_connect_local(b200sdr_ctx *ctx, b200sdr_ctx *const *peers /* world ctxs */);
+B200SDR_API int32_t b200sdr_split_spectrum_dev(b200sdr_ctx *ctx, const uint8_t *iq_slice_dev, uint64_t len_slice,
+                                               uint64_t frames_total, float *spectrum_dev);
+B200SDR_API int32_t b200sdr_exchange_wait(b200sdr_ctx *ctx);
+B200SDR_API int32_t b200sdr_exchange_destroy(b200sdr_ctx *ctx);
+
 B200SDR_API uint64_t b200sdr_spectrum_frames(uint64_t len_bytes);  /* floor((L-1024)/512)+1, 0 if L<1024 */
 B200SDR_API uint64_t b200sdr_wbfm_disc_len(uint64_t len_bytes);    /* ceil(L/10)                          */
 B200SDR_API uint64_t b200sdr_wbfm_audio_len(uint64_t len_bytes);   /* ceil(ceil(L/10)/5)                  */

@@ -421,6 +421,41 @@ class B200Sdr:
         self._check(fn(self.ctx, src, spectra.shape[0], db_min, db_max, img.ctypes.data), "b200sdr_render_waterfall")
         return img
 
+    # -- split-capture exchange (one capture across the GPUs of a box) ----------------------------
+    def exchange_create(self, world, rank):
+        """-> the 64-byte IPC handle of this rank's mailbox (gather them, pass to exchange_connect)."""
+        fn = self.lib.b200sdr_exchange_create
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        h = (C.c_uint8 * 64)()
+        self._check(fn(self.ctx, world, rank, h), "b200sdr_exchange_create")
+        return bytes(h)
+
+    def exchange_connect(self, handles):
+        fn = self.lib.b200sdr_exchange_connect
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_char_p]
+        self._check(fn(self.ctx, b"".join(handles)), "b200sdr_exchange_connect")
+
+    def exchange_connect_local(self, peers):
+        fn = self.lib.b200sdr_exchange_connect_local
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]
+        arr = (C.c_void_p * len(peers))(*[p.ctx for p in peers])
+        self._check(fn(self.ctx, arr), "b200sdr_exchange_connect_local")
+
+    def split_spectrum_dev(self, iq_slice_dev, len_slice, frames_total, spectrum_dev):
+        fn = self.lib.b200sdr_split_spectrum_dev
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        self._check(fn(self.ctx, iq_slice_dev, len_slice, frames_total, spectrum_dev), "b200sdr_split_spectrum_dev")
+
+    def exchange_wait(self):
+        fn = self.lib.b200sdr_exchange_wait
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p]
+        self._check(fn(self.ctx), "b200sdr_exchange_wait")
+
+    def exchange_destroy(self):
+        fn = self.lib.b200sdr_exchange_destroy
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p]
+        self._check(fn(self.ctx), "b200sdr_exchange_destroy")
+
     def synth_fill_dev(self, iq_dev, n_captures, len_each, kind, first_capture=0):
         self._check(self.lib.b200sdr_synth_fill_dev(self.ctx, iq_dev, n_captures, len_each, kind, first_capture), "b200sdr_synth_fill_dev")
 

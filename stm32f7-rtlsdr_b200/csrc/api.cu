@@ -23,6 +23,7 @@
 #include "misc_kernels.cuh"
 #include "plan.h"
 #include "render.cuh"
+#include "exchange.cuh"
 
 namespace {
 
@@ -50,7 +51,7 @@ struct b200sdr_ctx {
 
     /* constants on the device */
     float *d_window[3] = {nullptr, nullptr, nullptr};
-    float2 *d_twiddle = nullptr;
+    float4 *d_lane_consts[3] = {nullptr, nullptr, nullptr}; /* k_spectrum's per-lane twiddles + window, one per window kind */
     float *d_lut = nullptr;
     float *d_thresholds = nullptr;
     std::vector<float> h_taps[5];
@@ -90,6 +91,14 @@ struct b200sdr_ctx {
     uint8_t *d_am_buf = nullptr; uint32_t am_left = 0; uint64_t am_chunks = 0;
     AmFrontState *d_amf_state = nullptr; AmBackState *d_amb_state = nullptr; AudioFifo am_fifo;
     float *d_am_env_stream = nullptr;
+
+    /* split-capture exchange (K6): own mailbox, the peers' mailboxes as mapped here, call counter */
+    float *d_mailbox = nullptr;
+    uint32_t *d_xchg_status = nullptr; /* pinned, mapped: the kernel raises it, the host reads it without a copy */
+    float *peer_mail[B200_XCHG_MAX_WORLD] = {nullptr};
+    bool peer_is_ipc[B200_XCHG_MAX_WORLD] = {false};
+    uint32_t xchg_world = 0, xchg_rank = 0, xchg_seq = 0;
+    bool xchg_connected = false;
 };
 
 namespace {
@@ -127,7 +136,7 @@ int ensure_floats(b200sdr_ctx *ctx, float **p, size_t *have, size_t want)
 /* ---- launches --------------------------------------------------------------------------- */
 int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t stride, uint64_t len_bytes,
                     bool ema, const float *carry, float carry_scale, float scale_override, bool use_scale_override,
-                    float *out_dev)
+                    float *out_dev, bool finalize = true)
 {
     b200::SpectrumPlan pl = b200::plan_spectrum(len_bytes, n_captures, (uint32_t)ctx->sm_count);
     if (pl.frames == 0) return B200SDR_OK;
@@ -138,8 +147,7 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     p.capture_stride = stride;
     p.frames = pl.frames;
     p.frames_per_warp = pl.frames_per_warp;
-    p.window = ctx->d_window[ctx->cfg.window];
-    p.twiddle = ctx->d_twiddle;
+    p.lane_consts = ctx->d_lane_consts[ctx->cfg.window];
     p.partials = ctx->d_partials;
     p.ctas_per_capture = pl.ctas_per_capture;
     p.ema_beta = ctx->cfg.ema_beta;
@@ -148,12 +156,14 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     if (ema) k_spectrum<true><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
     else k_spectrum<false><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
     CU(cudaGetLastError());
+    ctx->launches += 1;
+    if (!finalize) return B200SDR_OK; /* the caller reduces ctx->d_partials itself (split-capture exchange) */
     float scale = ema ? 1.0f : 1.0f / (float)pl.frames;
     if (use_scale_override) scale = scale_override;
     k_spectrum_finalize<<<dim3(4, n_captures), 256, 0, ctx->s_compute>>>(ctx->d_partials, pl.ctas_per_capture, scale,
                                                                          carry, carry_scale, out_dev);
     CU(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
     return B200SDR_OK;
 }
 
@@ -498,10 +508,12 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
         CK(cudaMemcpy(ctx->d_window[w], ctx->h_window[w].data(), 1024 * sizeof(float), cudaMemcpyHostToDevice));
     }
     {
-        std::vector<float2> tw(1024);
-        b200::fill_twiddles(tw.data());
-        CK(cudaMalloc((void **)&ctx->d_twiddle, 1024 * sizeof(float2)));
-        CK(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
+        std::vector<float> lc(32 * B200_SPEC_LANE_CONSTS);
+        for (unsigned w = 0; w < 3; ++w) {
+            b200::fill_lane_consts(ctx->h_window[w].data(), lc.data());
+            CK(cudaMalloc((void **)&ctx->d_lane_consts[w], lc.size() * sizeof(float)));
+            CK(cudaMemcpy(ctx->d_lane_consts[w], lc.data(), lc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
         CK(cudaMalloc((void **)&ctx->d_lut, (B200SDR_SYNTH_LUT_SIZE + 1) * sizeof(float)));
         CK(cudaMemcpy(ctx->d_lut, synth_lut_host(), (B200SDR_SYNTH_LUT_SIZE + 1) * sizeof(float), cudaMemcpyHostToDevice));
         FmTaps ft{};
@@ -558,6 +570,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (!ctx) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->d_mailbox) b200sdr_exchange_destroy(ctx);
     for (auto e : ctx->ev_copied) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_consumed) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -570,7 +583,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     void *dev_ptrs[] = {ctx->d_ring, ctx->d_spec_buf, ctx->d_bounce, ctx->d_spec_acc, ctx->d_fm_buf, ctx->d_am_buf,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
-                        ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
+                        ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_lane_consts[0], ctx->d_lane_consts[1], ctx->d_lane_consts[2],
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
                         ctx->d_res_am};
     for (void *p : dev_ptrs) if (p) cudaFree(p);
@@ -1023,6 +1036,136 @@ int32_t b200sdr_synth_fill_host(uint8_t *iq_host, uint32_t n_captures, uint64_t 
         const uint64_t seed = B200SDR_SYNTH_SEED_BASE + first_capture + c;
         for (uint64_t n = 0; n < len_each / 2; ++n) b200sdr_synth_sample(lut, kind, seed, n, &p[2 * n], &p[2 * n + 1]);
     }
+    return B200SDR_OK;
+}
+
+/* ---- split-capture exchange (kernel K6) -------------------------------- */
+int32_t b200sdr_exchange_create(b200sdr_ctx *ctx, uint32_t world, uint32_t rank, uint8_t *handle_out64)
+{
+    if (!ctx) return B200SDR_FAIL;
+    if (world < 1 || world > B200_XCHG_MAX_WORLD || rank >= world) return fail(ctx, B200SDR_NOT_SUPPORTED, "bad world / rank");
+    if (ctx->d_mailbox) return fail(ctx, B200SDR_FAIL, "exchange already created");
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = B200_XCHG_MAILBOX_BYTES(world);
+    CU(cudaMalloc((void **)&ctx->d_mailbox, bytes));
+    CU(cudaMemset(ctx->d_mailbox, 0, bytes));
+    CU(cudaHostAlloc((void **)&ctx->d_xchg_status, sizeof(uint32_t), cudaHostAllocMapped));
+    *ctx->d_xchg_status = 0;
+    ctx->xchg_world = world;
+    ctx->xchg_rank = rank;
+    ctx->xchg_seq = 0;
+    ctx->xchg_connected = false;
+    for (uint32_t r = 0; r < B200_XCHG_MAX_WORLD; ++r) { ctx->peer_mail[r] = nullptr; ctx->peer_is_ipc[r] = false; }
+    ctx->peer_mail[rank] = ctx->d_mailbox;
+    if (handle_out64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ctx->d_mailbox));
+        memcpy(handle_out64, &h, 64);
+    }
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_exchange_connect(b200sdr_ctx *ctx, const uint8_t *handles /* world x 64 bytes, rank order */)
+{
+    if (!ctx || !handles) return B200SDR_FAIL;
+    if (!ctx->d_mailbox) return fail(ctx, B200SDR_FAIL, "call b200sdr_exchange_create first");
+    DeviceGuard guard(ctx->device);
+    for (uint32_t r = 0; r < ctx->xchg_world; ++r) {
+        if (r == ctx->xchg_rank || ctx->peer_mail[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64u * r, 64);
+        void *ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_mail[r] = (float *)ptr;
+        ctx->peer_is_ipc[r] = true;
+    }
+    ctx->xchg_connected = true;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_exchange_connect_local(b200sdr_ctx *ctx, b200sdr_ctx *const *peers /* world contexts of THIS process */)
+{
+    if (!ctx || !peers) return B200SDR_FAIL;
+    if (!ctx->d_mailbox) return fail(ctx, B200SDR_FAIL, "call b200sdr_exchange_create first");
+    DeviceGuard guard(ctx->device);
+    for (uint32_t r = 0; r < ctx->xchg_world; ++r) {
+        if (r == ctx->xchg_rank) continue;
+        b200sdr_ctx *o = peers[r];
+        if (!o || !o->d_mailbox || o->xchg_world != ctx->xchg_world || o->xchg_rank != r)
+            return fail(ctx, B200SDR_NOT_SUPPORTED, "peer context has no matching exchange");
+        if (o->device != ctx->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, ctx->device, o->device));
+            if (!can) return fail(ctx, B200SDR_NOT_SUPPORTED, "no peer access between the two devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "cudaDeviceEnablePeerAccess", e);
+        }
+        ctx->peer_mail[r] = o->d_mailbox;
+    }
+    ctx->xchg_connected = true;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_split_spectrum_dev(b200sdr_ctx *ctx, const uint8_t *iq_slice_dev, uint64_t len_slice, uint64_t frames_total,
+                                   float *spectrum_dev)
+{
+    if (!ctx || !spectrum_dev || (!iq_slice_dev && len_slice)) return B200SDR_FAIL;
+    if (!ctx->xchg_connected) return fail(ctx, B200SDR_FAIL, "exchange not connected");
+    if ((len_slice & 3u) || ((uintptr_t)iq_slice_dev & 1u) || frames_total == 0 || ctx->cfg.avg_mode != B200SDR_AVG_MEAN)
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "split capture: mean averaging, slice length a multiple of 4");
+    DeviceGuard guard(ctx->device);
+    /* this rank's frames -> per-CTA partial sums (no finalize: the exchange kernel reduces them) */
+    b200::SpectrumPlan pl = b200::plan_spectrum(len_slice, 1, (uint32_t)ctx->sm_count);
+    int rc = launch_spectrum(ctx, iq_slice_dev, 1, len_slice, len_slice, false, nullptr, 0.0f, 0.0f, false, nullptr, false);
+    if (rc) return rc;
+    ExchangeParams p{};
+    p.partials = ctx->d_partials;
+    p.ctas_per_capture = pl.frames ? pl.ctas_per_capture : 0; /* a rank without frames contributes zeros */
+    p.scale = 1.0f / (float)frames_total;
+    p.out = spectrum_dev;
+    for (uint32_t r = 0; r < ctx->xchg_world; ++r) p.mail[r] = ctx->peer_mail[r];
+    p.world = ctx->xchg_world;
+    p.rank = ctx->xchg_rank;
+    p.seq = ++ctx->xchg_seq;
+    p.status = ctx->d_xchg_status;
+    p.timeout_cycles = 10000000000ll; /* ~5 s at 1.965 GHz: a peer that never arrives fails the call */
+    k_spectrum_finalize_exchange<<<B200_XCHG_CTAS, 256, 0, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_exchange_wait(b200sdr_ctx *ctx)
+{
+    if (!ctx) return B200SDR_FAIL;
+    if (!ctx->d_xchg_status) return fail(ctx, B200SDR_FAIL, "no exchange");
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    if (*(volatile uint32_t *)ctx->d_xchg_status) {
+        *ctx->d_xchg_status = 0;
+        return fail(ctx, B200SDR_FAIL, "split-capture exchange timed out: a peer did not arrive");
+    }
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_exchange_destroy(b200sdr_ctx *ctx)
+{
+    if (!ctx) return B200SDR_FAIL;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->s_compute);
+    for (uint32_t r = 0; r < B200_XCHG_MAX_WORLD; ++r) {
+        if (ctx->peer_is_ipc[r] && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
+        ctx->peer_mail[r] = nullptr;
+        ctx->peer_is_ipc[r] = false;
+    }
+    if (ctx->d_mailbox) cudaFree(ctx->d_mailbox);
+    if (ctx->d_xchg_status) cudaFreeHost(ctx->d_xchg_status);
+    ctx->d_mailbox = nullptr;
+    ctx->d_xchg_status = nullptr;
+    ctx->xchg_connected = false;
+    ctx->xchg_world = 0;
     return B200SDR_OK;
 }
 

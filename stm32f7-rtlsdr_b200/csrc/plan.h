@@ -36,13 +36,18 @@ inline SpectrumPlan plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint3
     SpectrumPlan pl{};
     pl.frames = (uint32_t)spectrum_frames(len_bytes);
     if (pl.frames == 0) return pl;
-    /* aim at >= 32 CTAs per SM over the whole batch (two are resident at a time: >= 16 waves, so the
-     * last partial wave costs a few percent at most), at most 256 frames per warp, at least 1 */
-    const uint64_t total_frames = (uint64_t)pl.frames * n_captures;
-    const uint64_t want_warps = (uint64_t)sm_count * 32 * B200_SPEC_WARPS;
-    uint64_t fpw = total_frames / want_warps;
-    if (fpw < 1) fpw = 1;
-    if (fpw > 256) fpw = 256;
+    /* frames per warp (1..256) from a two-term cost model: a CTA costs a fixed prologue/epilogue
+     * (constants to registers, partial-sum reduction) plus fpw frames; two CTAs are resident per SM, so
+     * the batch runs in ceil(CTAs / (2 SMs)) waves.  Few frames per warp waste time in prologues (a single
+     * 10 s capture at fpw = 2 took 247 us), too many leave SMs idle in the last wave.  Units: 0.1 us. */
+    const uint64_t slots = (uint64_t)sm_count * B200_SPEC_MINB;
+    const uint64_t kCtaFixed = 30, kPerFrame = 13; /* ~3 us per CTA, ~1.3 us per frame with 2 warps per scheduler */
+    uint64_t best_cost = ~0ull, fpw = 1;
+    for (uint64_t f = 1; f <= 256; ++f) {
+        const uint64_t ctas = ceil_div(pl.frames, f * B200_SPEC_WARPS) * n_captures;
+        const uint64_t cost = ceil_div(ctas, slots) * (kCtaFixed + f * kPerFrame);
+        if (cost <= best_cost) { best_cost = cost; fpw = f; } /* ties: more frames per warp = fewer partials */
+    }
     pl.frames_per_warp = (uint32_t)fpw;
     pl.ctas_per_capture = (uint32_t)ceil_div(pl.frames, fpw * B200_SPEC_WARPS);
     return pl;
@@ -122,12 +127,24 @@ inline void fill_am_taps(AmTaps &t)
     for (int i = 0; i < B200_AMB_PER; ++i) t.rho_i[i] = (float)std::pow(rho, i + 1);
 }
 
-inline void fill_twiddles(float2 *tw1024)
+/* The per-lane constants of k_spectrum, in the order its two fused first stages consume them
+ * (out: 32 lanes x B200_SPEC_LANE_CONSTS floats).  For lane t and butterfly i, e = bitrev5(2 i):
+ *   floats 4 i .. 4 i + 3        = W^{e t} (re, im), W^{(e+16) t} (re, im),  W = e^{-2 pi i / 1024}
+ *   floats 64 + 2 i, 64 + 2 i + 1 = w[t + 32 e], w[t + 32 (e + 16)]          (the frame's window) */
+inline void fill_lane_consts(const float *window1024, float *out)
 {
-    for (int m = 0; m < 1024; ++m) {
-        const double a = -2.0 * kPi * m / 1024.0;
-        tw1024[m].x = (float)std::cos(a);
-        tw1024[m].y = (float)std::sin(a);
+    for (int t = 0; t < 32; ++t) {
+        float *row = out + t * B200_SPEC_LANE_CONSTS;
+        for (int i = 0; i < 16; ++i) {
+            const int x = 2 * i; /* e = the 5-bit reversal of 2 i */
+            const int e = ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+            for (int h = 0; h < 2; ++h) {
+                const double a = -2.0 * kPi * (double)(((e + 16 * h) * t) & 1023) / 1024.0;
+                row[4 * i + 2 * h] = (float)std::cos(a);
+                row[4 * i + 2 * h + 1] = (float)std::sin(a);
+                row[64 + 2 * i + h] = window1024[t + 32 * (e + 16 * h)];
+            }
+        }
     }
 }
 

@@ -233,6 +233,7 @@ static inline unsigned __ldg(const unsigned *p) { return *p; }
 static inline unsigned short __ldg(const unsigned short *p) { return *p; }
 static inline uint4 __ldg(const uint4 *p) { return *p; }
 static inline float2 __ldg(const float2 *p) { return *p; }
+static inline float4 __ldg(const float4 *p) { return *p; }
 static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 

@@ -97,3 +97,79 @@ def test_split_capture_on_device(sh, sdr_lib):
             part = torch.from_numpy(s.spectrum(iq[b0:b1])[0].copy())
             acc += sh.allreduce_split_spectrum(part, f1 - f0, frames, None)
     assert np.max(np.abs(acc.numpy().astype(np.float64) - whole) / whole) <= 1e-5
+
+
+def _run_fused_exchange(sh, sdr_lib, g, ctxs, iq):
+    """every 'rank' = one context: slice -> fused finalize + peer-memory all-reduce -> 1024 floats each"""
+    world = len(ctxs)
+    frames = (iq.size // 2 - 1024) // 512 + 1
+    bufs, outs = [], []
+    for r, s in enumerate(ctxs):  # allocations first: cudaMalloc may wait for kernels already spinning
+        b0, b1, f0, f1 = sh.split_capture_bytes(iq.size, r, world)
+        d_in = s.dev_alloc(max(b1 - b0, 16))
+        d_out = s.dev_alloc(4096)
+        if b1 > b0:
+            s.lib.b200sdr_copy_to_dev(s.ctx, d_in, iq[b0:b1].ctypes.data, b1 - b0)
+        bufs.append((d_in, d_out, b1 - b0))
+    for s, (d_in, d_out, n) in zip(ctxs, bufs):
+        s.split_spectrum_dev(d_in, n, frames, d_out)          # asynchronous: rank r+1 is launched while r waits
+    bufs = [(a, b) for a, b, _ in bufs]
+    for s, (d_in, d_out) in zip(ctxs, bufs):
+        s.exchange_wait()
+        outs.append(s.to_host(d_out, 4096, np.float32).copy())
+        s.dev_free(d_in)
+        s.dev_free(d_out)
+    return outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 4, 7])
+def test_fused_finalize_exchange_on_one_device(sh, sdr_lib, world):
+    """The fused finalize + all-reduce kernel (K6) with the ranks as contexts of ONE device: the
+    peer mailboxes are then plain device pointers, the protocol (push, flags, bounded wait, rank-order
+    sum, parity double-buffering over repeated calls) is the one used across NVLink."""
+    g = Golden()
+    ctxs = [sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) for _ in range(world)]
+    try:
+        for r, s in enumerate(ctxs):
+            s.exchange_create(world, r)
+        for s in ctxs:
+            s.exchange_connect_local(ctxs)
+            # grow the per-context workspace now: on ONE device a cudaFree inside a later call would wait
+            # for the other "ranks'" spinning kernels (separate processes / devices do not have this coupling)
+            s.spectrum(np.zeros(8 * 262144, np.uint8))
+        for rnd, nbytes in enumerate((4 * 262144, 262144 + 4096, 2048 + 1024 * 3, 8 * 262144)):
+            iq = g.synth(1, nbytes, SYNTH_MULTITONE, 30 + rnd)
+            whole, frames = g.spectrum(iq)
+            outs = _run_fused_exchange(sh, sdr_lib, g, ctxs, iq)
+            for o in outs[1:]:
+                assert np.array_equal(o, outs[0])             # bitwise the same on every rank
+            err = np.abs(outs[0].astype(np.float64) - whole)
+            bound = 1e-5 * whole + (4e-7 * np.sqrt(whole * whole.max()) if frames < 200 else 0.0)
+            assert np.all(err <= bound), (rnd, float(np.max(err / whole)))
+    finally:
+        for s in ctxs:
+            s.close()
+
+
+@pytest.mark.gpu
+def test_fused_exchange_times_out_instead_of_hanging(sdr_lib):
+    """A peer that never arrives: the kernel's wait is bounded, exchange_wait reports FAIL."""
+    import time
+    a, b = sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM), sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM)
+    try:
+        a.exchange_create(2, 0)
+        b.exchange_create(2, 1)
+        a.exchange_connect_local([a, b])
+        b.exchange_connect_local([a, b])
+        d_in, d_out = a.dev_alloc(4096), a.dev_alloc(4096)
+        t0 = time.time()
+        a.split_spectrum_dev(d_in, 4096, 7, d_out)             # rank 1 never calls
+        with pytest.raises(sdr_lib.B200SdrError) as ei:
+            a.exchange_wait()
+        assert ei.value.status == sdr_lib.FAIL and 2.0 < time.time() - t0 < 30.0
+        a.dev_free(d_in)
+        a.dev_free(d_out)
+    finally:
+        a.close()
+        b.close()
