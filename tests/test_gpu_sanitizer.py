@@ -25,6 +25,14 @@ SCRIPT = textwrap.dedent("""
                 s.sync()
         s.get_spectrum(); s.get_audio(pkg.CHAIN_WBFM); s.get_audio(pkg.CHAIN_AM)
         s.render_spectrum(None, 0.0, 100.0)
+        s.render_waterfall(s.spectrum(iq[:65536 * 3], 3), 0.0, 100.0)
+        # fused finalize + exchange kernel with a world of one (the sanitizer serialises kernels, so a
+        # multi-rank wait cannot be run under it)
+        s.exchange_create(1, 0); s.exchange_connect([b""])
+        d_in, d_out = s.dev_alloc(65536), s.dev_alloc(4096)
+        s.lib.b200sdr_copy_to_dev(s.ctx, d_in, iq.ctypes.data, 65536)
+        s.split_spectrum_dev(d_in, 65536, 63, d_out); s.exchange_wait()
+        s.dev_free(d_in); s.dev_free(d_out)
     print("SANITIZED_RUN_OK")
 """) % ROOT
 
