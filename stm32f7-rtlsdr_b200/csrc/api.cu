@@ -1068,8 +1068,9 @@ int32_t b200sdr_exchange_create(b200sdr_ctx *ctx, uint32_t world, uint32_t rank,
 
 int32_t b200sdr_exchange_connect(b200sdr_ctx *ctx, const uint8_t *handles /* world x 64 bytes, rank order */)
 {
-    if (!ctx || !handles) return B200SDR_FAIL;
+    if (!ctx) return B200SDR_FAIL;
     if (!ctx->d_mailbox) return fail(ctx, B200SDR_FAIL, "call b200sdr_exchange_create first");
+    if (!handles && ctx->xchg_world > 1) return fail(ctx, B200SDR_FAIL, "no IPC handles");
     DeviceGuard guard(ctx->device);
     for (uint32_t r = 0; r < ctx->xchg_world; ++r) {
         if (r == ctx->xchg_rank || ctx->peer_mail[r]) continue;
