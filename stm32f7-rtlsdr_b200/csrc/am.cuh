@@ -88,7 +88,9 @@ struct AmFrontParams {
     uint32_t n_tiles, total_chunks, tiles_per_segment;
     float *env;           /* [capture][env_stride] r[q]                                          */
     uint64_t env_stride;
-    AmFrontState *state;  /* optional (streaming, single segment)                                */
+    const AmFrontState *state; /* optional (streaming): carried state, read by segment 0            */
+    AmFrontState *state_out;   /* optional: written by the LAST segment (another buffer than `state`
+                                  when the launch has several segments: they run concurrently)      */
 };
 
 template <int J>
@@ -149,14 +151,16 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
 #pragma unroll
     for (int k = 0; k < 40; ++k) g[k] = taps->g1[k];
 
+    /* segment 0 continues the stream exactly; later segments rebuild the FIR state from one pre-roll tile */
+    const AmFrontState *st_in = (p.state && seg == 0) ? p.state + capture : nullptr;
     if (tid < 4) {
         float tr = 0.0f, ti = 0.0f;
-        if (p.state) { tr = p.state[capture].tail[2 * tid]; ti = p.state[capture].tail[2 * tid + 1]; }
+        if (st_in) { tr = st_in->tail[2 * tid]; ti = st_in->tail[2 * tid + 1]; }
         s_tailc[4 + tid] = c2_make(tr, ti);
     }
     for (int i = tid; i < B200_AM_NP * 12; i += B200_AM_THREADS) {
         float yr = 0.0f, yi = 0.0f;
-        if (p.state) { yr = p.state[capture].part[2 * i]; yi = p.state[capture].part[2 * i + 1]; }
+        if (st_in) { yr = st_in->part[2 * i]; yi = st_in->part[2 * i + 1]; }
         s_carry[i] = c2_make(yr, yi);
     }
 
@@ -264,20 +268,21 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
         /* the next tile's S1/S2 order these writes before their readers and before row d is rewritten */
     }
 
-    if (p.state) {
+    if (p.state_out && seg + 1 == gridDim.x) {
+        AmFrontState *st_out = p.state_out + capture;
         __syncthreads();
         const int fin = my_tiles ? (int)((my_tiles - 1) & 1) : 1;
         if (tid < 4) {
             float tr, ti;
             c2_get(s_tailc[fin * 4 + tid], tr, ti);
-            p.state[capture].tail[2 * tid] = tr;
-            p.state[capture].tail[2 * tid + 1] = ti;
+            st_out->tail[2 * tid] = tr;
+            st_out->tail[2 * tid + 1] = ti;
         }
         for (int i = tid; i < B200_AM_NP * 12; i += B200_AM_THREADS) {
             float yr, yi;
             c2_get(s_carry[i], yr, yi);
-            p.state[capture].part[2 * i] = yr;
-            p.state[capture].part[2 * i + 1] = yi;
+            st_out->part[2 * i] = yr;
+            st_out->part[2 * i + 1] = yi;
         }
     }
 }

@@ -86,10 +86,13 @@ struct b200sdr_ctx {
     uint64_t spec_frames = 0;
     /* streaming: WBFM */
     uint8_t *d_fm_buf = nullptr; uint32_t fm_left = 0; uint64_t fm_chunks = 0;
-    FmState *d_fm_state = nullptr; AudioFifo fm_fifo;
+    FmState *d_fm_state = nullptr;  /* two FmState: a launch reads [cur] and writes [cur ^ 1] (its segments run concurrently) */
+    int fm_state_cur = 0; AudioFifo fm_fifo;
     /* streaming: AM */
     uint8_t *d_am_buf = nullptr; uint32_t am_left = 0; uint64_t am_chunks = 0;
-    AmFrontState *d_amf_state = nullptr; AmBackState *d_amb_state = nullptr; AudioFifo am_fifo;
+    AmFrontState *d_amf_state = nullptr; /* two, ping-pong like d_fm_state */
+    int amf_state_cur = 0;
+    AmBackState *d_amb_state = nullptr; AudioFifo am_fifo;
     float *d_am_env_stream = nullptr;
 
     /* split-capture exchange (K6): own mailbox, the peers' mailboxes as mapped here, call counter */
@@ -258,14 +261,19 @@ int stream_wbfm(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     p.m_base = ctx->fm_chunks * B200_FM_OPT;
     p.total_chunks = n_chunks;
     p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_FM_THREADS);
-    p.tiles_per_segment = p.n_tiles;
+    /* a block of several tiles is spread over CTAs: segment 0 continues the carried state exactly, the
+     * others pre-roll one tile (plan.h), so a 256 KiB block costs 3 tile times instead of 9 */
+    p.tiles_per_segment = b200::kFmStreamTilesPerSegment;
+    const uint32_t segments = (uint32_t)b200::ceil_div(p.n_tiles, p.tiles_per_segment);
     const uint64_t a0 = b200::ceil_div(p.m_base, B200_FM_D2), a1 = b200::ceil_div(p.m_base + p.m1, B200_FM_D2);
     const uint32_t n_audio = (uint32_t)(a1 - a0);
     int frc = fifo_reserve(ctx, ctx->fm_fifo, n_audio, &p.audio);
     if (frc) return frc;
     p.audio_base = a0;
-    p.state = ctx->d_fm_state;
-    k_wbfm<<<dim3(1, 1), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_compute>>>(p);
+    p.state = ctx->d_fm_state + ctx->fm_state_cur;
+    p.state_out = ctx->d_fm_state + (ctx->fm_state_cur ^ 1);
+    ctx->fm_state_cur ^= 1;
+    k_wbfm<<<dim3(segments, 1), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_compute>>>(p);
     CU(cudaGetLastError());
     ctx->launches += 1;
     ctx->fm_fifo.count += n_audio;
@@ -294,10 +302,13 @@ int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     p.q_count = n_chunks;
     p.total_chunks = n_chunks;
     p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_AM_THREADS);
-    p.tiles_per_segment = p.n_tiles;
+    p.tiles_per_segment = b200::kFmStreamTilesPerSegment; /* spread over CTAs like stream_wbfm (FIRs only: exact) */
+    const uint32_t segments = (uint32_t)b200::ceil_div(p.n_tiles, p.tiles_per_segment);
     p.env = ctx->d_am_env_stream;
-    p.state = ctx->d_amf_state;
-    k_am_front<<<dim3(1, 1), B200_AM_THREADS, B200_AM_SMEM_BYTES, ctx->s_compute>>>(p);
+    p.state = ctx->d_amf_state + ctx->amf_state_cur;
+    p.state_out = ctx->d_amf_state + (ctx->amf_state_cur ^ 1);
+    ctx->amf_state_cur ^= 1;
+    k_am_front<<<dim3(segments, 1), B200_AM_THREADS, B200_AM_SMEM_BYTES, ctx->s_compute>>>(p);
     CU(cudaGetLastError());
     AmBackParams b{};
     b.env = ctx->d_am_env_stream;
@@ -324,8 +335,10 @@ int reset_stream_state(b200sdr_ctx *ctx)
     ctx->fm_left = 0; ctx->fm_chunks = 0; ctx->fm_fifo.count = 0; ctx->fm_fifo.head = 0;
     ctx->am_left = 0; ctx->am_chunks = 0; ctx->am_fifo.count = 0; ctx->am_fifo.head = 0;
     CU(cudaMemsetAsync(ctx->d_spec_acc, 0, 1024 * sizeof(float), ctx->s_compute));
-    CU(cudaMemsetAsync(ctx->d_fm_state, 0, sizeof(FmState), ctx->s_compute));
-    CU(cudaMemsetAsync(ctx->d_amf_state, 0, sizeof(AmFrontState), ctx->s_compute));
+    CU(cudaMemsetAsync(ctx->d_fm_state, 0, 2 * sizeof(FmState), ctx->s_compute));
+    ctx->fm_state_cur = 0;
+    CU(cudaMemsetAsync(ctx->d_amf_state, 0, 2 * sizeof(AmFrontState), ctx->s_compute));
+    ctx->amf_state_cur = 0;
     CU(cudaMemsetAsync(ctx->d_amb_state, 0, sizeof(AmBackState), ctx->s_compute));
     return B200SDR_OK;
 }
@@ -543,8 +556,8 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     CK(cudaMalloc((void **)&ctx->d_spec_acc, 1024 * sizeof(float)));
     CK(cudaMalloc((void **)&ctx->d_fm_buf, (size_t)cfg.slot_bytes + kFmLeftMax + 64));
     CK(cudaMalloc((void **)&ctx->d_am_buf, (size_t)cfg.slot_bytes + kAmLeftMax + 64));
-    CK(cudaMalloc((void **)&ctx->d_fm_state, sizeof(FmState)));
-    CK(cudaMalloc((void **)&ctx->d_amf_state, sizeof(AmFrontState)));
+    CK(cudaMalloc((void **)&ctx->d_fm_state, 2 * sizeof(FmState)));
+    CK(cudaMalloc((void **)&ctx->d_amf_state, 2 * sizeof(AmFrontState)));
     CK(cudaMalloc((void **)&ctx->d_amb_state, sizeof(AmBackState)));
     CK(cudaMalloc((void **)&ctx->d_am_env_stream, ((size_t)cfg.slot_bytes / 400 + 8) * sizeof(float)));
     ctx->fm_fifo.capacity = cfg.audio_capacity;

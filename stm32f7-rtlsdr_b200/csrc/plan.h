@@ -54,6 +54,8 @@ inline SpectrumPlan plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint3
 }
 
 /* ---- WBFM ---- */
+/* streaming launches: tiles per CTA.  2 keeps the pre-roll overhead at one extra tile per two. */
+constexpr uint32_t kFmStreamTilesPerSegment = 2;
 struct FmPlan {
     uint32_t n_tiles, total_chunks, tiles_per_segment, segments;
     uint64_t m1;

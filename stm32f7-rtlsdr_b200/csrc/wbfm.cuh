@@ -107,7 +107,9 @@ struct FmParams {
     uint64_t audio_base;     /* audio index of local p = 0 (streaming FIFO offset)                     */
     float *disc;             /* optional [capture][disc_stride]                                        */
     uint64_t disc_stride;
-    FmState *state;          /* optional [capture]: read at start, written at the end (1 segment only) */
+    const FmState *state;    /* optional [capture]: carried state, read by segment 0 (later segments pre-roll) */
+    FmState *state_out;      /* optional [capture]: written by the LAST segment; a different buffer than
+                                `state` when the launch has more than one segment (they run concurrently) */
     uint32_t *n_audio_out;   /* optional [capture]: number of audio samples written (streaming)        */
 };
 
@@ -221,20 +223,22 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
     float lane_pow = 1.0f; /* (a^12)^lane */
     for (int i = 0; i < lane; ++i) lane_pow *= taps->a12;
 
-    /* carried state */
+    /* carried state: segment 0 continues the stream exactly; later segments start from zero one tile
+     * early (FIR memory is 80 samples, the de-emphasis pole decays to 1e-37 over a tile) */
+    const FmState *st_in = (p.state && seg == 0) ? p.state + capture : nullptr;
     if (tid < 8) {
         float tr = 0.0f, ti = 0.0f;
-        if (p.state) { tr = p.state[capture].tail[2 * tid]; ti = p.state[capture].tail[2 * tid + 1]; }
+        if (st_in) { tr = st_in->tail[2 * tid]; ti = st_in->tail[2 * tid + 1]; }
         s_tailc[8 + tid] = c2_make(tr, ti); /* tile 0 reads carry buffer 1 */
     }
     if (tid == 8) {
         float yr = 0.0f, yi = 0.0f;
-        if (p.state) { yr = p.state[capture].ylast[0]; yi = p.state[capture].ylast[1]; }
+        if (st_in) { yr = st_in->ylast[0]; yi = st_in->ylast[1]; }
         s_ylastc[1] = c2_make(yr, yi);
     }
-    if (tid == 9) s_wsum[4] = p.state ? p.state[capture].e_last : 0.0f; /* tile carry e[m0-1] */
+    if (tid == 9) s_wsum[4] = st_in ? st_in->e_last : 0.0f; /* tile carry e[m0-1] */
     if (tid >= 32 && tid < 32 + B200_FM_HIST)
-        s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32] = p.state ? p.state[capture].e_hist[tid - 32] : 0.0f;
+        s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32] = st_in ? st_in->e_hist[tid - 32] : 0.0f;
 
     auto issue_tile = [&](uint32_t it) { /* thread 0 only */
         const uint32_t tile = t_begin + it;
@@ -383,24 +387,25 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         /* the next tile's S1..S3 order these writes before their readers */
     }
 
-    if (p.state) {
+    if (p.state_out && seg + 1 == gridDim.x) {
+        FmState *st_out = p.state_out + capture;
         __syncthreads();
         const int fin = my_tiles ? (int)((my_tiles - 1) & 1) : 1; /* carry buffer written last */
         if (tid < 8) {
             float tr, ti;
             c2_get(s_tailc[fin * 8 + tid], tr, ti);
-            p.state[capture].tail[2 * tid] = tr;
-            p.state[capture].tail[2 * tid + 1] = ti;
+            st_out->tail[2 * tid] = tr;
+            st_out->tail[2 * tid + 1] = ti;
         }
         if (tid == 8) {
             float yr, yi;
             c2_get(s_ylastc[fin], yr, yi);
-            p.state[capture].ylast[0] = yr;
-            p.state[capture].ylast[1] = yi;
+            st_out->ylast[0] = yr;
+            st_out->ylast[1] = yi;
         }
-        if (tid == 9) p.state[capture].e_last = s_wsum[4];
+        if (tid == 9) st_out->e_last = s_wsum[4];
         if (tid >= 32 && tid < 32 + B200_FM_HIST)
-            p.state[capture].e_hist[tid - 32] = s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32];
+            st_out->e_hist[tid - 32] = s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32];
     }
 }
 

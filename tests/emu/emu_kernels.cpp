@@ -6,6 +6,7 @@
  */
 #include "cuda_emu.h"
 
+#include <cstring>
 #include <vector>
 
 #include "../../stm32f7-rtlsdr_b200/csrc/plan.h"
@@ -76,7 +77,7 @@ int emu_wbfm_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_byt
 /* WBFM streaming step: `n_chunks` whole 120-sample chunks starting at stream chunk index
  * `chunk_base`, exact state carried in *state (FmState, zero it before the first call). */
 int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, void *state, float *audio,
-                    uint32_t *n_audio, float *disc)
+                    uint32_t *n_audio, float *disc, uint32_t tiles_per_segment)
 {
     b200::fill_fm_taps(c_fm_taps);
     FmParams p{};
@@ -87,14 +88,18 @@ int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, v
     p.m_base = chunk_base * B200_FM_OPT;
     p.total_chunks = n_chunks;
     p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_FM_THREADS);
-    p.tiles_per_segment = p.n_tiles ? p.n_tiles : 1;
+    p.tiles_per_segment = tiles_per_segment ? tiles_per_segment : (p.n_tiles ? p.n_tiles : 1); /* 0: one segment */
+    const uint32_t segments = p.n_tiles ? (uint32_t)b200::ceil_div(p.n_tiles, p.tiles_per_segment) : 1;
     p.audio = audio;
     p.audio_stride = 0;
     p.audio_base = b200::ceil_div(p.m_base, B200_FM_D2);
     p.disc = disc;
     p.disc_stride = 0;
-    p.state = (FmState *)state;
-    emu::launch(dim3(1, 1), dim3(B200_FM_THREADS), B200_FM_SMEM_BYTES, [&] { k_wbfm(p); });
+    FmState next{}; /* segments run "concurrently": the state is double-buffered like in the product */
+    p.state = (const FmState *)state;
+    p.state_out = &next;
+    emu::launch(dim3(segments, 1), dim3(B200_FM_THREADS), B200_FM_SMEM_BYTES, [&] { k_wbfm(p); });
+    memcpy(state, &next, sizeof next);
     *n_audio = (uint32_t)(b200::ceil_div(p.m_base + p.m1, B200_FM_D2) - p.audio_base);
     return 0;
 }
@@ -140,7 +145,7 @@ int emu_am_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
 
 /* AM streaming step over n_chunks whole 200-sample chunks starting at stream chunk `chunk_base` */
 int emu_am_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, void *fstate, void *bstate, float *audio,
-                  uint32_t *n_audio)
+                  uint32_t *n_audio, uint32_t tiles_per_segment)
 {
     b200::fill_am_taps(c_am_taps);
     std::vector<float> env(n_chunks + 1);
@@ -150,10 +155,14 @@ int emu_am_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, voi
     p.q_count = n_chunks;
     p.total_chunks = n_chunks;
     p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_AM_THREADS);
-    p.tiles_per_segment = p.n_tiles ? p.n_tiles : 1;
+    p.tiles_per_segment = tiles_per_segment ? tiles_per_segment : (p.n_tiles ? p.n_tiles : 1); /* 0: one segment */
+    const uint32_t segments = p.n_tiles ? (uint32_t)b200::ceil_div(p.n_tiles, p.tiles_per_segment) : 1;
     p.env = env.data();
-    p.state = (AmFrontState *)fstate;
-    emu::launch(dim3(1, 1), dim3(B200_AM_THREADS), B200_AM_SMEM_BYTES, [&] { k_am_front(p); });
+    AmFrontState next{};
+    p.state = (const AmFrontState *)fstate;
+    p.state_out = &next;
+    emu::launch(dim3(segments, 1), dim3(B200_AM_THREADS), B200_AM_SMEM_BYTES, [&] { k_am_front(p); });
+    memcpy(fstate, &next, sizeof next);
     AmBackParams b{};
     b.env = env.data();
     b.q_count = n_chunks;

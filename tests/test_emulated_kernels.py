@@ -19,9 +19,9 @@ def emu():
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     e.emu_spectrum.argtypes = [vp, u32, u64, vp, u32, C.c_int, C.c_float, vp]
     e.emu_wbfm_batch.argtypes = [vp, u32, u64, u32, vp, vp]
-    e.emu_wbfm_stream.argtypes = [vp, u32, u64, vp, vp, vp, vp]
+    e.emu_wbfm_stream.argtypes = [vp, u32, u64, vp, vp, vp, vp, u32]
     e.emu_am_batch.argtypes = [vp, u32, u64, u32, vp, vp]
-    e.emu_am_stream.argtypes = [vp, u32, u64, vp, vp, vp, vp]
+    e.emu_am_stream.argtypes = [vp, u32, u64, vp, vp, vp, vp, u32]
     return e
 
 
@@ -75,7 +75,10 @@ def test_wbfm_kernel_logic(emu, g, n, ncap, tps):
         assert np.max(np.abs(audio[c * m2:(c + 1) * m2] - ga)) < 1e-5
 
 
-def test_wbfm_streaming_state_carry(emu, g):
+@pytest.mark.parametrize("tps", [0, 1, 2])
+def test_wbfm_streaming_state_carry(emu, g, tps):
+    """tps = tiles per segment of every streaming launch (0: one CTA walks the whole block; otherwise
+    the block is split over CTAs: segment 0 continues the carried state, the others pre-roll a tile)"""
     nch = 700
     n = 120 * nch
     iq = padded(g.synth(1, 2 * n, SYNTH_WBFM, 3))
@@ -90,7 +93,7 @@ def test_wbfm_streaming_state_carry(emu, g):
         a = np.zeros(k * 12 // 5 + 2, np.float32)
         d = np.zeros(k * 12, np.float32)
         na = C.c_uint32(0)
-        emu.emu_wbfm_stream(iq[pos * 240:].ctypes.data, k, pos, state.ctypes.data, a.ctypes.data, C.byref(na), d.ctypes.data)
+        emu.emu_wbfm_stream(iq[pos * 240:].ctypes.data, k, pos, state.ctypes.data, a.ctypes.data, C.byref(na), d.ctypes.data, tps)
         outa.append(a[: na.value])
         outd.append(d)
         pos += k
@@ -115,7 +118,8 @@ def test_am_kernel_logic_and_segment_invariance(emu, g, n, ncap):
             assert np.max(np.abs(audio[c * m3:(c + 1) * m3] - g.am(iq[c * nb:(c + 1) * nb]))) < 1e-6
 
 
-def test_am_streaming_state_carry(emu, g):
+@pytest.mark.parametrize("tps", [0, 1, 2])
+def test_am_streaming_state_carry(emu, g, tps):
     nch = 500
     n = 200 * nch
     iq = padded(g.synth(1, 2 * n, SYNTH_AM, 3))
@@ -130,7 +134,7 @@ def test_am_streaming_state_carry(emu, g):
         k = int(min(k, nch - pos))
         a = np.zeros(k + 2, np.float32)
         na = C.c_uint32(0)
-        emu.emu_am_stream(iq[pos * 400:].ctypes.data, k, pos, fs.ctypes.data, bs.ctypes.data, a.ctypes.data, C.byref(na))
+        emu.emu_am_stream(iq[pos * 400:].ctypes.data, k, pos, fs.ctypes.data, bs.ctypes.data, a.ctypes.data, C.byref(na), tps)
         outa.append(a[: na.value])
         pos += k
     outa = np.concatenate(outa)
