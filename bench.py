@@ -172,6 +172,70 @@ def bind_to_gpu_numa_node(gpu_index):
 
 
 # ---------------------------------------------------------------------------------------- GPU arm
+def split_capture_probe(pkg, sharding, sdr, dist, torch, rank, world):
+    """One 10 s capture split in time over the ranks: every rank runs k_spectrum over its own
+    frames and ONE kernel reduces the partial sums, pushes them to every peer over NVLink peer memory and
+    adds the ranks' contributions in rank order.  Returns a small dict for the JSON line.  Every rank
+    makes the same sequence of collective calls whatever fails locally (failures are agreed on with an
+    all-reduce), so a problem here can never desynchronise the rest of the benchmark."""
+    def all_ok(ok):
+        f = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
+
+    err, handle = "", None
+    try:
+        handle = sdr.exchange_create(world, rank)
+    except Exception as e:
+        err = str(e)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)                                  # plumbing: 64-byte IPC handles
+    try:
+        if any(h is None for h in handles):
+            raise RuntimeError(err or "a peer could not create its mailbox")
+        sdr.exchange_connect(handles)
+        cap = torch.empty(CAPTURE_BYTES, dtype=torch.uint8, device="cuda")
+        out = torch.zeros(1024, dtype=torch.float32, device="cuda")
+        whole = torch.empty(1024, dtype=torch.float32, device="cuda")
+        sdr.synth_fill_dev(cap.data_ptr(), 1, CAPTURE_BYTES, pkg.SYNTH_MULTITONE, first_capture=999)  # same capture everywhere
+        sdr.batch_spectrum_dev(cap.data_ptr(), 1, CAPTURE_BYTES, whole.data_ptr())                   # single-GPU answer
+        sdr.sync()
+        ok = True
+    except Exception as e:
+        err, ok = str(e), False
+    if not all_ok(ok):
+        return {"error": ("setup: " + err)[:300]}
+    frames = (CAPTURE_SAMPLES - 1024) // 512 + 1
+    b0, b1, _, _ = sharding.split_capture_bytes(CAPTURE_BYTES, rank, world)
+    iters, dt = 20, 0.0
+    try:
+        for i in range(3 + iters):
+            if i == 3:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            sdr.split_spectrum_dev(cap.data_ptr() + b0, b1 - b0, frames, out.data_ptr())
+            sdr.exchange_wait()                                              # bounded: FAIL after ~5 s, never a hang
+        dt = (time.perf_counter() - t0) / iters
+    except Exception as e:
+        err, ok = str(e), False
+    if not all_ok(ok):
+        return {"error": ("exchange: " + err)[:300]}
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gathered = [torch.zeros_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    rel = float(((out - whole).abs() / whole).max())
+    try:
+        sdr.exchange_destroy()
+    except Exception:
+        pass
+    return {"what": "one 10 s capture split over the ranks: k_spectrum on each slice + ONE fused finalize / NVLink "
+                    "peer-memory all-reduce kernel (no library collective)",
+            "us_per_capture": float(t.item()) * 1e6, "MSps": CAPTURE_SAMPLES / float(t.item()) / 1e6,
+            "bitwise_identical_on_all_ranks": bool(same), "max_rel_diff_vs_single_gpu_spectrum": rel}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,6 +356,13 @@ def main():
     am_bytes = 2.0 + 4.0 * 8000.0 / 2400000.0
     am_gbs = am_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e9
 
+    # ---- N > 1 only, informative: the one exchange step the path can have -- ONE 10 s capture split in time
+    # across the ranks, bin sums combined by the fused finalize + NVLink peer-memory all-reduce kernel
+    # (csrc/exchange.cuh).  Not part of `value`; a failure here is reported, never fatal. --------------------
+    split = None
+    if world > 1:
+        split = split_capture_probe(pkg, sharding, sdr, dist, torch, rank, world)
+
     # ---- end to end through the host-buffer entry point --------------------------------------
     E = min(args.e2e_captures, B)
     hp, h_iq = sdr.pinned_alloc(E * CAPTURE_BYTES)
@@ -393,6 +464,8 @@ def main():
             "ingest": ingest,
             "cpu_baseline": cpu,
         }
+        if split is not None:
+            line["split_capture"] = split
         print(json.dumps(line))
     sdr.close()
     if world > 1:
