@@ -27,9 +27,8 @@
 
 namespace {
 
-constexpr uint32_t kCarryMax = 2048;         /* spectrum carry: < 1024 samples                    */
-constexpr uint32_t kFmLeftMax = 240;         /* < one 120-sample chunk                            */
-constexpr uint32_t kAmLeftMax = 400;         /* < one 200-sample chunk                            */
+constexpr uint64_t kStreamSlack = 16384;     /* device stream buffer = ring_slots x slot_bytes + this; the unread
+                                                tail carried over a wrap is < 2048 + 400 bytes           */
 constexpr uint64_t kWaveBytesDefault = 192ull << 20;
 
 struct AudioFifo {
@@ -67,29 +66,31 @@ struct b200sdr_ctx {
 
     /* ingest ring */
     uint8_t *h_ring = nullptr;          /* pinned: ring_slots x slot_bytes                          */
-    uint8_t *d_ring = nullptr;          /* device mirror of the slots                               */
+    /* device side of the ring: ONE linear stream buffer.  Every submitted slot is copied behind the
+     * previous one, each chain keeps its own read offset, so the kernels see [leftover | new block]
+     * contiguously without any device-to-device copy; at the end of the buffer the small unread tail is
+     * moved to the front (once per ring_slots submits). */
+    uint8_t *d_stream = nullptr;
+    uint64_t stream_cap = 0, wpos = 0, spec_off = 0, fm_off = 0, am_off = 0, last_pos = 0;
+    cudaEvent_t ev_wrapped = nullptr;
     std::vector<cudaEvent_t> ev_copied;   /* H2D of slot done (pinned slot reusable)                */
-    std::vector<cudaEvent_t> ev_consumed; /* chains have taken the device slot                      */
     std::vector<uint8_t> slot_used;
     uint32_t ring_head = 0;
     bool slot_acquired = false;
     uint32_t pending = 0;               /* bytes appended to slot ring_head, not yet submitted      */
     uint32_t submit_bytes = 0;          /* submit the open slot once this many bytes are pending    */
     uint64_t bytes_in = 0, blocks_in = 0, busy_returns = 0, submits = 0;
-    uint32_t last_len = 0, last_off = 0, last_slot = 0;
+    uint32_t last_len = 0, last_off = 0;
 
     /* streaming: spectrum */
-    uint8_t *d_spec_buf = nullptr;  /* [carry | block]                                              */
-    uint8_t *d_bounce = nullptr;
-    uint32_t spec_have = 0;         /* bytes currently in d_spec_buf                                */
     float *d_spec_acc = nullptr;    /* running sum (mean) or EMA state, 1024 floats                 */
     uint64_t spec_frames = 0;
     /* streaming: WBFM */
-    uint8_t *d_fm_buf = nullptr; uint32_t fm_left = 0; uint64_t fm_chunks = 0;
+    uint64_t fm_chunks = 0;
     FmState *d_fm_state = nullptr;  /* two FmState: a launch reads [cur] and writes [cur ^ 1] (its segments run concurrently) */
     int fm_state_cur = 0; AudioFifo fm_fifo;
     /* streaming: AM */
-    uint8_t *d_am_buf = nullptr; uint32_t am_left = 0; uint64_t am_chunks = 0;
+    uint64_t am_chunks = 0;
     AmFrontState *d_amf_state = nullptr; /* two, ping-pong like d_fm_state */
     int amf_state_cur = 0;
     AmBackState *d_amb_state = nullptr; AudioFifo am_fifo;
@@ -226,36 +227,29 @@ int launch_am_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
 bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where);
 
-/* ---- streaming steps (all on the compute stream, after the block is in d_ring[slot]) ---- */
-int stream_spectrum(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
+/* ---- streaming steps: all on the compute stream, after the new bytes are in d_stream[.. wpos) ---- */
+int stream_spectrum(b200sdr_ctx *ctx)
 {
-    CU(cudaMemcpyAsync(ctx->d_spec_buf + ctx->spec_have, d_block, len, cudaMemcpyDeviceToDevice, ctx->s_compute));
-    ctx->spec_have += len;
-    const uint64_t frames = b200::spectrum_frames(ctx->spec_have);
+    const uint64_t have = ctx->wpos - ctx->spec_off;
+    const uint64_t frames = b200::spectrum_frames(have);
     if (frames == 0) return B200SDR_OK;
     const bool ema = ctx->cfg.avg_mode == B200SDR_AVG_EMA;
     /* mean: acc += sum |X|^2 ; EMA: acc = (1-beta)^F acc + sum beta (1-beta)^(F-1-m) |X_m|^2 */
     const float carry_scale = ema ? powf(1.0f - ctx->cfg.ema_beta, (float)frames) : 1.0f;
-    int rc = launch_spectrum(ctx, ctx->d_spec_buf, 1, 0, ctx->spec_have, ema, ctx->d_spec_acc, carry_scale, 1.0f, true,
+    int rc = launch_spectrum(ctx, ctx->d_stream + ctx->spec_off, 1, 0, have, ema, ctx->d_spec_acc, carry_scale, 1.0f, true,
                              ctx->d_spec_acc);
     if (rc) return rc;
     ctx->spec_frames += frames;
-    const uint32_t consumed = (uint32_t)(frames * 1024u); /* 512 samples x 2 bytes per frame */
-    const uint32_t keep = ctx->spec_have - consumed;
-    CU(cudaMemcpyAsync(ctx->d_bounce, ctx->d_spec_buf + consumed, keep, cudaMemcpyDeviceToDevice, ctx->s_compute));
-    CU(cudaMemcpyAsync(ctx->d_spec_buf, ctx->d_bounce, keep, cudaMemcpyDeviceToDevice, ctx->s_compute));
-    ctx->spec_have = keep;
+    ctx->spec_off += frames * 1024u; /* 512 samples x 2 bytes per frame; the 512-sample overlap stays unread */
     return B200SDR_OK;
 }
 
-int stream_wbfm(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
+int stream_wbfm(b200sdr_ctx *ctx)
 {
-    CU(cudaMemcpyAsync(ctx->d_fm_buf + ctx->fm_left, d_block, len, cudaMemcpyDeviceToDevice, ctx->s_compute));
-    const uint32_t have = ctx->fm_left + len;
-    const uint32_t n_chunks = have / (2 * B200_FM_CHUNK);
-    if (n_chunks == 0) { ctx->fm_left = have; return B200SDR_OK; }
+    const uint32_t n_chunks = (uint32_t)((ctx->wpos - ctx->fm_off) / (2 * B200_FM_CHUNK));
+    if (n_chunks == 0) return B200SDR_OK;
     FmParams p{};
-    p.iq = ctx->d_fm_buf;
+    p.iq = ctx->d_stream + ctx->fm_off; /* 16-byte aligned: offsets move by whole 240-byte chunks and 16-byte wraps */
     p.capture_bytes = (uint64_t)n_chunks * 2 * B200_FM_CHUNK;
     p.m1 = (uint64_t)n_chunks * B200_FM_OPT;
     p.m_base = ctx->fm_chunks * B200_FM_OPT;
@@ -278,26 +272,21 @@ int stream_wbfm(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     ctx->launches += 1;
     ctx->fm_fifo.count += n_audio;
     ctx->fm_chunks += n_chunks;
-    const uint32_t consumed = n_chunks * 2 * B200_FM_CHUNK;
-    ctx->fm_left = have - consumed;
-    if (ctx->fm_left)
-        CU(cudaMemcpyAsync(ctx->d_fm_buf, ctx->d_fm_buf + consumed, ctx->fm_left, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    ctx->fm_off += (uint64_t)n_chunks * 2 * B200_FM_CHUNK;
     return B200SDR_OK;
 }
 
-int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
+int stream_am(b200sdr_ctx *ctx)
 {
-    CU(cudaMemcpyAsync(ctx->d_am_buf + ctx->am_left, d_block, len, cudaMemcpyDeviceToDevice, ctx->s_compute));
-    const uint32_t have = ctx->am_left + len;
-    const uint32_t n_chunks = have / (2 * B200_AM_CHUNK);
-    if (n_chunks == 0) { ctx->am_left = have; return B200SDR_OK; }
+    const uint32_t n_chunks = (uint32_t)((ctx->wpos - ctx->am_off) / (2 * B200_AM_CHUNK));
+    if (n_chunks == 0) return B200SDR_OK;
     const uint64_t a0 = (2 * ctx->am_chunks + 2) / 3, a1 = (2 * (ctx->am_chunks + n_chunks) + 2) / 3;
     const uint32_t n_audio = (uint32_t)(a1 - a0);
     float *am_out = nullptr;
     int frc = fifo_reserve(ctx, ctx->am_fifo, n_audio, &am_out);
     if (frc) return frc;
     AmFrontParams p{};
-    p.iq = ctx->d_am_buf;
+    p.iq = ctx->d_stream + ctx->am_off;
     p.capture_bytes = (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
     p.q_count = n_chunks;
     p.total_chunks = n_chunks;
@@ -322,18 +311,16 @@ int stream_am(b200sdr_ctx *ctx, const uint8_t *d_block, uint32_t len)
     ctx->launches += 2;
     ctx->am_fifo.count += n_audio;
     ctx->am_chunks += n_chunks;
-    const uint32_t consumed = n_chunks * 2 * B200_AM_CHUNK;
-    ctx->am_left = have - consumed;
-    if (ctx->am_left)
-        CU(cudaMemcpyAsync(ctx->d_am_buf, ctx->d_am_buf + consumed, ctx->am_left, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    ctx->am_off += (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
     return B200SDR_OK;
 }
 
 int reset_stream_state(b200sdr_ctx *ctx)
 {
-    ctx->spec_have = 0; ctx->spec_frames = 0;
-    ctx->fm_left = 0; ctx->fm_chunks = 0; ctx->fm_fifo.count = 0; ctx->fm_fifo.head = 0;
-    ctx->am_left = 0; ctx->am_chunks = 0; ctx->am_fifo.count = 0; ctx->am_fifo.head = 0;
+    ctx->wpos = ctx->spec_off = ctx->fm_off = ctx->am_off = ctx->last_pos = 0;
+    ctx->spec_frames = 0;
+    ctx->fm_chunks = 0; ctx->fm_fifo.count = 0; ctx->fm_fifo.head = 0;
+    ctx->am_chunks = 0; ctx->am_fifo.count = 0; ctx->am_fifo.head = 0;
     CU(cudaMemsetAsync(ctx->d_spec_acc, 0, 1024 * sizeof(float), ctx->s_compute));
     CU(cudaMemsetAsync(ctx->d_fm_state, 0, 2 * sizeof(FmState), ctx->s_compute));
     ctx->fm_state_cur = 0;
@@ -355,22 +342,46 @@ const float *synth_lut_host()
     return lut;
 }
 
+/* end of the stream buffer: move the unread tail (what the slowest enabled chain has not consumed:
+ * < 2048 + 400 bytes) to the front and rebase all offsets by a multiple of 16 bytes (TMA alignment) */
+int wrap_stream(b200sdr_ctx *ctx)
+{
+    uint64_t lo = ctx->wpos;
+    if ((ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM) && ctx->spec_off < lo) lo = ctx->spec_off;
+    if ((ctx->cfg.chains & B200SDR_CHAIN_WBFM) && ctx->fm_off < lo) lo = ctx->fm_off;
+    if ((ctx->cfg.chains & B200SDR_CHAIN_AM) && ctx->am_off < lo) lo = ctx->am_off;
+    const uint64_t shift = lo & ~(uint64_t)15, tail = ctx->wpos - shift;
+    if (shift < tail) return fail(ctx, B200SDR_FAIL, "stream buffer too small for the unread tail");
+    /* on the compute stream the move is ordered after every kernel that read the old data; the H2D copies
+     * that follow (copy stream) wait for it */
+    if (tail) CU(cudaMemcpyAsync(ctx->d_stream, ctx->d_stream + shift, tail, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    CU(cudaEventRecord(ctx->ev_wrapped, ctx->s_compute));
+    CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_wrapped, 0));
+    ctx->wpos -= shift;
+    ctx->spec_off = ctx->spec_off > shift ? ctx->spec_off - shift : 0;
+    ctx->fm_off = ctx->fm_off > shift ? ctx->fm_off - shift : 0;
+    ctx->am_off = ctx->am_off > shift ? ctx->am_off - shift : 0;
+    ctx->last_pos = ctx->last_pos > shift ? ctx->last_pos - shift : 0;
+    return B200SDR_OK;
+}
+
 int commit_slot(b200sdr_ctx *ctx, uint32_t slot, uint32_t len)
 {
     uint8_t *h_slot = ctx->h_ring + (size_t)slot * ctx->cfg.slot_bytes;
-    uint8_t *d_slot = ctx->d_ring + (size_t)slot * ctx->cfg.slot_bytes;
-    /* the device slot may still be read by the chains of `ring_slots` blocks ago */
-    if (ctx->slot_used[slot]) CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_consumed[slot], 0));
-    CU(cudaMemcpyAsync(d_slot, h_slot, len, cudaMemcpyHostToDevice, ctx->s_copy));
+    if (ctx->wpos + len > ctx->stream_cap) {
+        int wrc = wrap_stream(ctx);
+        if (wrc) return wrc;
+    }
+    CU(cudaMemcpyAsync(ctx->d_stream + ctx->wpos, h_slot, len, cudaMemcpyHostToDevice, ctx->s_copy));
     CU(cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy));
     CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[slot], 0));
+    ctx->last_pos = ctx->wpos;
+    ctx->wpos += len;
     int rc = B200SDR_OK;
-    if (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM) { rc = stream_spectrum(ctx, d_slot, len); if (rc) return rc; }
-    if (ctx->cfg.chains & B200SDR_CHAIN_WBFM) { rc = stream_wbfm(ctx, d_slot, len); if (rc) return rc; }
-    if (ctx->cfg.chains & B200SDR_CHAIN_AM) { rc = stream_am(ctx, d_slot, len); if (rc) return rc; }
-    CU(cudaEventRecord(ctx->ev_consumed[slot], ctx->s_compute));
+    if (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM) { rc = stream_spectrum(ctx); if (rc) return rc; }
+    if (ctx->cfg.chains & B200SDR_CHAIN_WBFM) { rc = stream_wbfm(ctx); if (rc) return rc; }
+    if (ctx->cfg.chains & B200SDR_CHAIN_AM) { rc = stream_am(ctx); if (rc) return rc; }
     ctx->slot_used[slot] = 1;
-    ctx->last_slot = slot;
     ctx->submits += 1;
     ctx->ring_head = (slot + 1) % ctx->cfg.ring_slots;
     return B200SDR_OK;
@@ -543,19 +554,15 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     /* ingest ring + streaming buffers */
     const size_t ring_bytes = (size_t)cfg.ring_slots * cfg.slot_bytes;
     CK(cudaHostAlloc((void **)&ctx->h_ring, ring_bytes, cudaHostAllocDefault));
-    CK(cudaMalloc((void **)&ctx->d_ring, ring_bytes));
+    ctx->stream_cap = (uint64_t)ring_bytes + kStreamSlack;
+    CK(cudaMalloc((void **)&ctx->d_stream, ctx->stream_cap));
+    CK(cudaEventCreateWithFlags(&ctx->ev_wrapped, cudaEventDisableTiming));
     ctx->ev_copied.resize(cfg.ring_slots);
-    ctx->ev_consumed.resize(cfg.ring_slots);
     ctx->slot_used.assign(cfg.ring_slots, 0);
     for (uint32_t i = 0; i < cfg.ring_slots; ++i) {
         CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
     }
-    CK(cudaMalloc((void **)&ctx->d_spec_buf, (size_t)cfg.slot_bytes + kCarryMax + 64));
-    CK(cudaMalloc((void **)&ctx->d_bounce, kCarryMax + 64));
     CK(cudaMalloc((void **)&ctx->d_spec_acc, 1024 * sizeof(float)));
-    CK(cudaMalloc((void **)&ctx->d_fm_buf, (size_t)cfg.slot_bytes + kFmLeftMax + 64));
-    CK(cudaMalloc((void **)&ctx->d_am_buf, (size_t)cfg.slot_bytes + kAmLeftMax + 64));
     CK(cudaMalloc((void **)&ctx->d_fm_state, 2 * sizeof(FmState)));
     CK(cudaMalloc((void **)&ctx->d_amf_state, 2 * sizeof(AmFrontState)));
     CK(cudaMalloc((void **)&ctx->d_amb_state, sizeof(AmBackState)));
@@ -585,7 +592,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     cudaDeviceSynchronize();
     if (ctx->d_mailbox) b200sdr_exchange_destroy(ctx);
     for (auto e : ctx->ev_copied) if (e) cudaEventDestroy(e);
-    for (auto e : ctx->ev_consumed) if (e) cudaEventDestroy(e);
+    if (ctx->ev_wrapped) cudaEventDestroy(ctx->ev_wrapped);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_wave_copied[i]) cudaEventDestroy(ctx->ev_wave_copied[i]);
         if (ctx->ev_wave_done[i]) cudaEventDestroy(ctx->ev_wave_done[i]);
@@ -594,7 +601,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
-    void *dev_ptrs[] = {ctx->d_ring, ctx->d_spec_buf, ctx->d_bounce, ctx->d_spec_acc, ctx->d_fm_buf, ctx->d_am_buf,
+    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_lane_consts[0], ctx->d_lane_consts[1], ctx->d_lane_consts[2],
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
@@ -743,7 +750,7 @@ int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capaci
     CU(cudaStreamSynchronize(ctx->s_copy));
     CU(cudaStreamSynchronize(ctx->s_compute));
     uint32_t n = ctx->last_len < capacity ? ctx->last_len : capacity;
-    if (n) CU(cudaMemcpy(out, ctx->d_ring + (size_t)ctx->last_slot * ctx->cfg.slot_bytes + ctx->last_off, n, cudaMemcpyDeviceToHost));
+    if (n) CU(cudaMemcpy(out, ctx->d_stream + ctx->last_pos + ctx->last_off, n, cudaMemcpyDeviceToHost));
     if (len) *len = ctx->last_len;
     return B200SDR_OK;
 }

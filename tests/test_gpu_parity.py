@@ -512,6 +512,36 @@ def test_streaming_tiny_blocks(sdr_lib, g, submit_bytes):
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
 
 
+@pytest.mark.parametrize("submit_bytes", [0, 4], ids=["coalesced", "per_block"])
+def test_streaming_wraps_the_device_stream_buffer_many_times(sdr_lib, g, submit_bytes):
+    """The device side of the ring is one linear buffer of ring_slots x slot_bytes (+ slack); with two
+    4 KiB slots a 400 KB stream wraps it about twenty times, each time carrying the unread tail of the
+    slowest chain to the front.  Results must not notice."""
+    total = 4 * 100_000
+    iq = g.synth(1, total, SYNTH_WBFM, 78)
+    with sdr_lib.B200Sdr(slot_bytes=4096, ring_slots=2, submit_bytes=submit_bytes) as s:
+        fm, am = [], []
+        pos = 0
+        for n in random_cuts(total, 4096, 11):
+            feed(s, iq[pos:pos + n], [n])
+            pos += n
+            if len(fm) * 7 % 5 == 0:
+                fm.append(s.get_audio(sdr_lib.CHAIN_WBFM))
+        fm.append(s.get_audio(sdr_lib.CHAIN_WBFM))
+        am.append(s.get_audio(sdr_lib.CHAIN_AM))
+        spec, frames = s.get_spectrum()
+        got, n = s.debug_last_block(16)
+        assert n > 0 and np.array_equal(got[:min(n, 16)], iq[total - n:total - n + min(n, 16)])
+    fm, am = np.concatenate(fm), np.concatenate(am)
+    gold, gframes = g.spectrum(iq)
+    assert frames == gframes
+    spec_check(spec, gold)
+    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_am = (2 * (total // 2 // 200) + 2) // 3
+    assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
+    assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
+
+
 def test_example_host_driver_runs(sdr_lib, g, tmp_path):
     """The C host driver (examples/host_driver.c): reference START/WAIT/COMPLETE cadence over the
     pinned ring; its audio files must equal the golden chains."""
