@@ -393,7 +393,8 @@ def main():
         src = pkg.synth_fill_host(1, blk * 16, pkg.SYNTH_WBFM, 0)
         n_blocks, busy = 512, 0
         for i in range(32):
-            s2.process_samples(src[(i % 16) * blk:(i % 16 + 1) * blk])
+            while s2.process_samples(src[(i % 16) * blk:(i % 16 + 1) * blk], allow_busy=True) == pkg.BUSY:
+                pass
         s2.sync()
         s2.get_audio(pkg.CHAIN_WBFM, 1 << 22)
         t0 = time.perf_counter()

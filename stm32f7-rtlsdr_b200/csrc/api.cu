@@ -50,7 +50,7 @@ struct b200sdr_ctx {
 
     /* constants on the device */
     float *d_window[3] = {nullptr, nullptr, nullptr};
-    float4 *d_lane_consts[3] = {nullptr, nullptr, nullptr}; /* k_spectrum's per-lane twiddles + window, one per window kind */
+    float2 *d_twiddle = nullptr;
     float *d_lut = nullptr;
     float *d_thresholds = nullptr;
     std::vector<float> h_taps[5];
@@ -151,7 +151,8 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     p.capture_stride = stride;
     p.frames = pl.frames;
     p.frames_per_warp = pl.frames_per_warp;
-    p.lane_consts = ctx->d_lane_consts[ctx->cfg.window];
+    p.window = ctx->d_window[ctx->cfg.window];
+    p.twiddle = ctx->d_twiddle;
     p.partials = ctx->d_partials;
     p.ctas_per_capture = pl.ctas_per_capture;
     p.ema_beta = ctx->cfg.ema_beta;
@@ -532,12 +533,10 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
         CK(cudaMemcpy(ctx->d_window[w], ctx->h_window[w].data(), 1024 * sizeof(float), cudaMemcpyHostToDevice));
     }
     {
-        std::vector<float> lc(32 * B200_SPEC_LANE_CONSTS);
-        for (unsigned w = 0; w < 3; ++w) {
-            b200::fill_lane_consts(ctx->h_window[w].data(), lc.data());
-            CK(cudaMalloc((void **)&ctx->d_lane_consts[w], lc.size() * sizeof(float)));
-            CK(cudaMemcpy(ctx->d_lane_consts[w], lc.data(), lc.size() * sizeof(float), cudaMemcpyHostToDevice));
-        }
+        std::vector<float2> tw(1024);
+        b200::fill_twiddles(tw.data());
+        CK(cudaMalloc((void **)&ctx->d_twiddle, 1024 * sizeof(float2)));
+        CK(cudaMemcpy(ctx->d_twiddle, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void **)&ctx->d_lut, (B200SDR_SYNTH_LUT_SIZE + 1) * sizeof(float)));
         CK(cudaMemcpy(ctx->d_lut, synth_lut_host(), (B200SDR_SYNTH_LUT_SIZE + 1) * sizeof(float), cudaMemcpyHostToDevice));
         FmTaps ft{};
@@ -603,7 +602,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
-                        ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_lane_consts[0], ctx->d_lane_consts[1], ctx->d_lane_consts[2],
+                        ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
                         ctx->d_res_am};
     for (void *p : dev_ptrs) if (p) cudaFree(p);

@@ -129,24 +129,12 @@ inline void fill_am_taps(AmTaps &t)
     for (int i = 0; i < B200_AMB_PER; ++i) t.rho_i[i] = (float)std::pow(rho, i + 1);
 }
 
-/* The per-lane constants of k_spectrum, in the order its two fused first stages consume them
- * (out: 32 lanes x B200_SPEC_LANE_CONSTS floats).  For lane t and butterfly i, e = bitrev5(2 i):
- *   floats 4 i .. 4 i + 3        = W^{e t} (re, im), W^{(e+16) t} (re, im),  W = e^{-2 pi i / 1024}
- *   floats 64 + 2 i, 64 + 2 i + 1 = w[t + 32 e], w[t + 32 (e + 16)]          (the frame's window) */
-inline void fill_lane_consts(const float *window1024, float *out)
+inline void fill_twiddles(float2 *tw1024)
 {
-    for (int t = 0; t < 32; ++t) {
-        float *row = out + t * B200_SPEC_LANE_CONSTS;
-        for (int i = 0; i < 16; ++i) {
-            const int x = 2 * i; /* e = the 5-bit reversal of 2 i */
-            const int e = ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
-            for (int h = 0; h < 2; ++h) {
-                const double a = -2.0 * kPi * (double)(((e + 16 * h) * t) & 1023) / 1024.0;
-                row[4 * i + 2 * h] = (float)std::cos(a);
-                row[4 * i + 2 * h + 1] = (float)std::sin(a);
-                row[64 + 2 * i + h] = window1024[t + 32 * (e + 16 * h)];
-            }
-        }
+    for (int m = 0; m < 1024; ++m) {
+        const double a = -2.0 * kPi * m / 1024.0;
+        tw1024[m].x = (float)std::cos(a);
+        tw1024[m].y = (float)std::sin(a);
     }
 }
 

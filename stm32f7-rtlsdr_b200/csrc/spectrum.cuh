@@ -12,25 +12,24 @@
  *   pass 1 (lane t):  Y[k1] = sum_j w[n] x[n] W32^{j k1}      in registers (fft32.cuh)
  *   twiddle:          Y[k1] *= W1024^{t k1}                    folded into pass 2's first stage
  *   transpose:        lane t -> lane k1 through a warp-private 32x34 shared tile
+ * The 32 window values and 32 twiddles a lane needs never change, so they are staged through shared
+ * memory once per CTA and then held in registers (250 registers, 2 CTAs of 4 warps per SM): the only
+ * shared-memory traffic per frame is the transpose (DESIGN.md 5.1 has the A/B measurements).
  *   pass 2 (lane k1): X[k1+32 k2] = sum_t Y_t[k1] W32^{t k2}   in registers
  *   power:            acc[k2] += |X|^2                          32 bins per lane, in registers
- * The 32 window values and 32 twiddles a lane needs never change, so they live in registers for the
- * whole kernel (96 of the 250 registers; 2 CTAs of 4 warps per SM), loaded straight from a 12 KB
- * per-lane table the host lays out once (plan.h fill_lane_consts): the only shared-memory traffic per
- * frame is the transpose.  DESIGN.md 5.1 has the A/B measurements behind these choices.
- *
  * A warp walks `frames_per_warp` consecutive frames (hop 512) and keeps the 32 x 32 bin sums in
  * registers; the warps of a CTA are then added in a fixed order and one 1024-float partial per
- * CTA goes to a workspace that k_spectrum_finalize (or the split-capture exchange kernel) sums in a
- * fixed order -> deterministic results, no float atomics.
+ * CTA goes to a workspace that k_spectrum_finalize sums in a fixed order -> deterministic
+ * results (no float atomics), identical for any GPU count.
  *
  * Input access: lane t reads the 2-byte sample n = t + 32 j straight from global memory
  * (a warp reads 64 contiguous bytes per j; both halves of every 128-byte line are used by
- * consecutive j, the second from L1), the loads of frame m+1 are issued before the FFT of frame m.
- * Every input byte is fetched from HBM once (the 50 % overlap re-read hits L2).
+ * consecutive j, the second from L1).  Every input byte is fetched from HBM once per frame
+ * pair at most (the 50 % overlap re-read hits L2).
  *
- * Roofline: 2 bytes per new complex sample vs 482 packed + 64 scalar FP instructions per frame
- * (512 new samples) -> bound by the scheduler issue port / FP32 pipe, not by HBM.
+ * Roofline: 2 bytes per new complex sample vs ~2100 fp32 lane-operations per frame (512 new
+ * samples) -> this chain is bound by the FP32 pipe, not by HBM; the packed
+ * FFMA2 formulation keeps the issue slots for loads / PRMT / LDS / STS free.
  */
 #ifndef B200_SPECTRUM_CUH
 #define B200_SPECTRUM_CUH
@@ -40,14 +39,40 @@
 #ifndef B200_SPEC_MINB
 #define B200_SPEC_MINB 2 /* CTAs per SM the register allocation is tuned for (8 warps/SM, up to 255 registers) */
 #endif
+#ifndef B200_SPEC_PREFETCH
+#define B200_SPEC_PREFETCH 1 /* issue the loads of frame m+1 before the FFT of frame m */
+#endif
+#ifndef B200_SPEC_FUSE_WIN
+#define B200_SPEC_FUSE_WIN 1 /* window multiply folded into the first butterfly stage of pass 1 */
+#endif
+#ifndef B200_SPEC_MERGE_TW
+#define B200_SPEC_MERGE_TW 1 /* fold the inter-pass twiddles into the first butterfly stage of pass 2 */
+#endif
+#ifndef B200_SPEC_REUSE
+#define B200_SPEC_REUSE 0 /* keep the upper 16 sample words of frame m in registers as the lower 16 of frame m+1 */
+#endif
+#ifndef B200_SPEC_REGCONST
+#define B200_SPEC_REGCONST 3 /* bit 0: this lane's 32 twiddles, bit 1: its 32 window values live in registers for the
+                                whole kernel instead of being re-read from shared memory every frame (needs MINB <= 2) */
+#endif
+/* TIMING EXPERIMENTS ONLY (results are wrong when non-zero; tools/gpu_variants.sh): bit 0 no window
+ * loads, bit 1 no twiddle loads, bit 2 no transpose, bit 3 no global loads */
+#ifndef B200_SPEC_EXPERIMENT
+#define B200_SPEC_EXPERIMENT 0
+#endif
 #define B200_SPEC_WARPS 4
 #define B200_SPEC_THREADS (32 * B200_SPEC_WARPS)
-#define B200_SPEC_XP 34 /* transpose tile row pitch in complex elements: rows are 16-byte aligned; the 64-bit
-                           stores and the 128-bit loads are both conflict-free */
-#define B200_SPEC_LANE_CONSTS 96 /* floats per lane: 16 twiddle pairs (float4 each) + 8 float4 of window values */
+#ifndef B200_SPEC_XP
+#define B200_SPEC_XP 34 /* transpose tile row pitch in complex elements: 64-bit accesses conflict-free.
+                           34 (even): rows are 16-byte aligned and are read back with 128-bit loads, also conflict-free */
+#endif
+#define B200_SPEC_WP 36 /* window row pitch in floats */
 
-/* shared memory: the warps' transpose tiles, re-used for the CTA reduction at the end */
-#define B200_SPEC_SMEM_BYTES (B200_SPEC_WARPS * 32 * B200_SPEC_XP * 8)
+/* shared memory carve-up (bytes) */
+#define B200_SPEC_SMEM_WIN 0
+#define B200_SPEC_SMEM_TW (32 * B200_SPEC_WP * 4)
+#define B200_SPEC_SMEM_XP (B200_SPEC_SMEM_TW + 32 * 32 * 8)
+#define B200_SPEC_SMEM_BYTES (B200_SPEC_SMEM_XP + B200_SPEC_WARPS * 32 * B200_SPEC_XP * 8)
 
 #ifdef B200_EMULATED
 #define B200_DYN_SMEM(name) unsigned char *name = EMU_DYN_SMEM
@@ -55,12 +80,19 @@
 #define B200_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #endif
 
+#if B200_SPEC_EXPERIMENT & 8
+#define B200_SPEC_LOAD(ptr) ((uint32_t)(uintptr_t)(ptr) * 2654435761u >> 16)
+#else
+#define B200_SPEC_LOAD(ptr) ((uint32_t)__ldg(ptr))
+#endif
+
 struct SpectrumParams {
     const uint8_t *iq;        /* capture c starts at iq + c * capture_stride                     */
     uint64_t capture_stride;  /* bytes                                                           */
     uint32_t frames;          /* frames per capture (all captures equal length)                  */
     uint32_t frames_per_warp; /* consecutive frames walked by one warp                           */
-    const float4 *lane_consts;/* [32 lanes][24 float4], plan.h fill_lane_consts                  */
+    const float *window;      /* 1024 floats                                                     */
+    const float2 *twiddle;    /* 1024 entries: e^{-2 pi i m / 1024}                              */
     float *partials;          /* [capture][ctas_per_capture][1024]                               */
     uint32_t ctas_per_capture;
     float ema_log2_decay;     /* log2(1 - beta), EMA only                                        */
@@ -71,21 +103,31 @@ template <bool EMA>
 __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(SpectrumParams p)
 {
     B200_DYN_SMEM(smem);
+    float *s_win = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_WIN);
+    c2 *s_tw = reinterpret_cast<c2 *>(smem + B200_SPEC_SMEM_TW);
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    c2 *s_xp = reinterpret_cast<c2 *>(smem) + warp * (32 * B200_SPEC_XP);
+    c2 *s_xp = reinterpret_cast<c2 *>(smem + B200_SPEC_SMEM_XP) + warp * (32 * B200_SPEC_XP);
 
-    /* this lane's constants -> registers, in the order the two fused first stages consume them:
-     *   r_tw[i]   = (W^{e t}, W^{(e+16) t}),  e = bitrev5(2 i): butterfly i of pass 2's first stage
-     *   r_win[i2] = (w_a, w_b) of butterflies 2 i2 and 2 i2 + 1 of pass 1's first stage,
-     *               w_a = w[t + 32 e], w_b = w[t + 32 (e + 16)] */
-    float4 r_tw[16], r_win[8];
-    {
-        const float4 *lc = p.lane_consts + lane * (B200_SPEC_LANE_CONSTS / 4);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r_tw[i] = __ldg(lc + i);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r_win[i] = __ldg(lc + 16 + i);
+    /* stage the window per lane in the order pass 1 consumes it: win[t][2 i + h] = w[t + 32 (e_i + 16 h)]
+     * with e_i = bitrev5(2 i) -- the two samples of first-stage butterfly i sit side by side --
+     * and the twiddles as pairs (see below) */
+    for (int i = tid; i < 1024; i += B200_SPEC_THREADS) {
+        int t = i & 31, j = i >> 5;
+        {
+            const int e = j & 15, h = j >> 4;
+            const int bi = b200_bitrev5(e) >> 1; /* butterfly index i with bitrev5(2 i) == e */
+            s_win[t * B200_SPEC_WP + 2 * bi + h] = __ldg(p.window + i);
+        }
+        float2 w = __ldg(p.twiddle + ((t * j) & 1023));
+#if B200_SPEC_MERGE_TW
+        /* pair layout: [e][lane] = (W^{e lane}, W^{(e+16) lane}), e = 0..15: one 16-byte load feeds a
+         * first-stage butterfly of pass 2 (elements e and e+16 of lane's column) */
+        s_tw[((j & 15) * 32 + t) * 2 + (j >> 4)] = c2_make(w.x, w.y);
+#else
+        s_tw[j * 32 + t] = c2_make(w.x, w.y);
+#endif
     }
+    __syncthreads();
 
     const uint32_t capture = blockIdx.y;
     const uint32_t warp_global = blockIdx.x * B200_SPEC_WARPS + (uint32_t)warp;
@@ -98,66 +140,120 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
     for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
 
     const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
+    const float *my_win = s_win + lane * B200_SPEC_WP;
+#if B200_SPEC_EXPERIMENT & 3
+    const float fake_w = my_win[0] + 0.5f;
+#endif
+#if B200_SPEC_REGCONST & 1
+    float4 r_tw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r_tw[i] = *reinterpret_cast<const float4 *>(s_tw + (b200_bitrev5(2 * i) * 32 + lane) * 2);
+#endif
+#if B200_SPEC_REGCONST & 2
+    float4 r_win[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r_win[i] = *reinterpret_cast<const float4 *>(my_win + 4 * i);
+#endif
 
     /* software pipeline: the 32 two-byte loads of frame m+1 are issued before the FFT of frame m,
-     * so no warp waits on HBM/L2 latency with only two warps per scheduler resident */
+     * so no warp ever waits on HBM/L2 latency with only three warps per scheduler resident */
     const unsigned short *src0 = reinterpret_cast<const unsigned short *>(cap) + (uint32_t)lane;
     uint32_t raw[32];
-    if (m_begin < m_end) {
+    if (B200_SPEC_PREFETCH && m_begin < m_end) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src0 + (uint64_t)m_begin * 512u + 32 * j);
+        for (int j = 0; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src0 + (uint64_t)m_begin * 512u + 32 * j);
     }
     for (uint32_t m = m_begin; m < m_end; ++m) {
         c2 v[32];
+        if (!B200_SPEC_PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src0 + (uint64_t)m * 512u + 32 * j);
+        }
         /* convert, window and first DIT stage of pass 1 in one go: butterfly i takes samples
          * e = bitrev5(2 i) and e + 16:  X = a wa + b wb,  Y = a wa - b wb  (3 packed ops) */
 #pragma unroll
         for (int i2 = 0; i2 < 8; ++i2) {
+#if B200_SPEC_EXPERIMENT & 1
+            const float4 w4 = make_float4(fake_w, fake_w, fake_w, fake_w);
+#elif B200_SPEC_REGCONST & 2
             const float4 w4 = r_win[i2];
+#else
+            const float4 w4 = *reinterpret_cast<const float4 *>(my_win + 4 * i2);
+#endif
             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii) {
                 const int i = 2 * i2 + ii, e = b200_bitrev5(2 * i);
                 const c2 pa = c2_scale(c2_from_u8_lo(raw[e]), wv[2 * ii]);
+#if B200_SPEC_FUSE_WIN
                 const c2 b = c2_from_u8_lo(raw[e + 16]);
                 v[2 * i] = c2_fma_s(b, wv[2 * ii + 1], pa);
                 v[2 * i + 1] = c2_fma_s(b, -wv[2 * ii + 1], pa);
+#else
+                const c2 pb = c2_scale(c2_from_u8_lo(raw[e + 16]), wv[2 * ii + 1]);
+                v[2 * i] = c2_add(pa, pb);
+                v[2 * i + 1] = c2_sub(pa, pb);
+#endif
             }
         }
-        if (m + 1 < m_end) {
+        if (B200_SPEC_PREFETCH && m + 1 < m_end) {
             const unsigned short *src = src0 + (uint64_t)(m + 1) * 512u;
+#if B200_SPEC_REUSE
+            /* samples t + 32 (j + 16) of frame m are samples t + 32 j of frame m + 1 (hop 512) */
 #pragma unroll
-            for (int j = 0; j < 32; ++j) raw[j] = (uint32_t)__ldg(src + 32 * j);
+            for (int j = 0; j < 16; ++j) raw[j] = raw[j + 16];
+#pragma unroll
+            for (int j = 16; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src + 32 * j);
+#else
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = B200_SPEC_LOAD(src + 32 * j);
+#endif
         }
         b200_stage_k<4, 0>::run(v);
         b200_stage_k<8, 0>::run(v);
         b200_stage_k<16, 0>::run(v);
         b200_stage_k<32, 0>::run(v); /* v[k1] = Y[k1] */
+#if !B200_SPEC_MERGE_TW
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+            float wr, wi;
+            c2_get(s_tw[k1 * 32 + lane], wr, wi);
+            v[k1] = c2_cmul(v[k1], wr, wi);
+        }
+#endif
         /* transpose through the warp-private tile: row = k1 (the reader's lane), column = source lane t.
          * The barrier that keeps this frame's stores behind the previous frame's loads sits HERE, a whole
          * pass later than those loads, so it never waits on them. */
+#if !(B200_SPEC_EXPERIMENT & 4)
         __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) s_xp[k1 * B200_SPEC_XP + lane] = v[k1];
         __syncwarp();
-#ifdef B200_PACKED_MATH
 #pragma unroll
+#if (B200_SPEC_XP % 2) == 0 && defined(B200_PACKED_MATH)
         for (int t = 0; t < 32; t += 2) {
             const float4 q = *reinterpret_cast<const float4 *>(s_xp + lane * B200_SPEC_XP + t);
             v[b200_bitrev5(t)] = c2_make(q.x, q.y);
             v[b200_bitrev5(t + 1)] = c2_make(q.z, q.w);
         }
 #else
-#pragma unroll
         for (int t = 0; t < 32; ++t) v[b200_bitrev5(t)] = s_xp[lane * B200_SPEC_XP + t];
 #endif
+#endif
+#if B200_SPEC_MERGE_TW
         /* first DIT stage of pass 2 with the four-step twiddles folded in: slots (2i, 2i+1) hold the
          * elements e = bitrev5(2i) < 16 and e + 16 of this lane's column; X = Ta a + Tb b, Y = Ta a - Tb b
          * = 2 (Ta a) - X: 5 packed ops instead of 2 + 2 (twiddles) + 2 (butterfly) */
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = b200_bitrev5(2 * i);
+#if B200_SPEC_EXPERIMENT & 2
+            const float4 tw = make_float4(fake_w, fake_w, fake_w, fake_w);
+#elif B200_SPEC_REGCONST & 1
             const float4 tw = r_tw[i];
+#else
+            const float4 tw = *reinterpret_cast<const float4 *>(s_tw + (e * 32 + lane) * 2);
+#endif
             const c2 pa = (e == 0) ? v[2 * i] : c2_cmul(v[2 * i], tw.x, tw.y);
             const c2 x = c2_cfma(v[2 * i + 1], tw.z, tw.w, pa);
             v[2 * i + 1] = c2_two_a_minus(pa, x);
@@ -167,6 +263,9 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         b200_stage_k<8, 0>::run(v);
         b200_stage_k<16, 0>::run(v);
         b200_stage_k<32, 0>::run(v); /* v[k2] = X[lane + 32 k2] */
+#else
+        b200_fft32(v); /* v[k2] = X[lane + 32 k2] */
+#endif
         if (EMA) {
             float wgt = p.ema_beta * exp2f((float)(p.frames - 1u - m) * p.ema_log2_decay);
 #pragma unroll
@@ -179,7 +278,7 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 
     /* fixed-order reduction over the CTA's warps, then one partial per CTA */
     __syncthreads();
-    float *s_red = reinterpret_cast<float *>(smem); /* [warp][1024], pitch 32*XP*2 floats */
+    float *s_red = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_XP); /* [warp][1024], pitch 32*XP*2 floats */
     float *mine = s_red + warp * (32 * B200_SPEC_XP * 2);
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) mine[k2 * 32 + lane] = acc[k2]; /* bin k = lane + 32 k2 */

@@ -19,8 +19,8 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
 {
     uint32_t frames = (uint32_t)b200::spectrum_frames(len_each_bytes);
     if (frames == 0) return -1;
-    std::vector<float4> lc(32 * B200_SPEC_LANE_CONSTS / 4);
-    b200::fill_lane_consts(window, reinterpret_cast<float *>(lc.data()));
+    std::vector<float2> tw(1024);
+    b200::fill_twiddles(tw.data());
     uint32_t frames_per_cta = frames_per_warp * B200_SPEC_WARPS;
     uint32_t ctas = (frames + frames_per_cta - 1) / frames_per_cta;
     std::vector<float> partials((size_t)n_captures * ctas * 1024);
@@ -29,7 +29,8 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
     p.capture_stride = len_each_bytes;
     p.frames = frames;
     p.frames_per_warp = frames_per_warp;
-    p.lane_consts = lc.data();
+    p.window = window;
+    p.twiddle = tw.data();
     p.partials = partials.data();
     p.ctas_per_capture = ctas;
     p.ema_beta = beta;
