@@ -443,7 +443,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_spectrum (+k_spectrum_finalize)", "achieved": spec_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": spec_gbs / hbm_peak,
-                         "traffic": 1.0224 * 2.0 * B * CAPTURE_SAMPLES,  # bytes per launch: ncu dram read+write = 1.0224 x algorithmic (profiles/r1_ncu_summary.txt: 1.5457 GB read + 24.6 MB written for 1.536 GB of input)
+                         "traffic": 1.0119 * 2.0 * B * CAPTURE_SAMPLES,  # bytes per launch: ncu dram read+write = 1.0119 x algorithmic (profiles/r1_ncu_summary.txt: 1.5424 GB read + 11.9 MB written for 1.536 GB of input)
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": 2.0,
                          "note": "FP32-pipe bound, not HBM bound (DESIGN.md 5.1): 1028 FP32-pipe cycles per 1024-pt frame per SM "
