@@ -12,11 +12,12 @@
  *   pass 1 (lane t):  Y[k1] = sum_j w[n] x[n] W32^{j k1}      in registers (fft32.cuh)
  *   twiddle:          Y[k1] *= W1024^{t k1}                    folded into pass 2's first stage
  *   transpose:        lane t -> lane k1 through a warp-private 32x34 shared tile
- * The 32 window values and 32 twiddles a lane needs never change, so they are staged through shared
- * memory once per CTA and then held in registers (250 registers, 2 CTAs of 4 warps per SM): the only
- * shared-memory traffic per frame is the transpose (DESIGN.md 5.1 has the A/B measurements).
  *   pass 2 (lane k1): X[k1+32 k2] = sum_t Y_t[k1] W32^{t k2}   in registers
  *   power:            acc[k2] += |X|^2                          32 bins per lane, in registers
+ * The 32 window values and 32 twiddles a lane needs never change, so they are staged through shared
+ * memory once per CTA and then held in registers (250 registers, 2 CTAs of 4 warps per SM): the only
+ * shared-memory traffic per frame is the transpose (DESIGN.md 5.1 has the A/B measurements; the
+ * compile-time knobs below are the A/B switches of those measurements, defaults = shipped).
  * A warp walks `frames_per_warp` consecutive frames (hop 512) and keeps the 32 x 32 bin sums in
  * registers; the warps of a CTA are then added in a fixed order and one 1024-float partial per
  * CTA goes to a workspace that k_spectrum_finalize sums in a fixed order -> deterministic
