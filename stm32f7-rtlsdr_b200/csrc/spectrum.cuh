@@ -20,8 +20,10 @@
  * compile-time knobs below are the A/B switches of those measurements, defaults = shipped).
  * A warp walks `frames_per_warp` consecutive frames (hop 512) and keeps the 32 x 32 bin sums in
  * registers; the warps of a CTA are then added in a fixed order and one 1024-float partial per
- * CTA goes to a workspace that k_spectrum_finalize sums in a fixed order -> deterministic
- * results (no float atomics), identical for any GPU count.
+ * CTA goes to a workspace that k_spectrum_finalize (or the split-capture exchange kernel) sums in a
+ * fixed order -> deterministic results, no float atomics: the same batch shape gives the same bits
+ * on every run and every GPU (the frames-per-warp split, hence the summation order, follows the
+ * batch shape, plan.h).
  *
  * Input access: lane t reads the 2-byte sample n = t + 32 j straight from global memory
  * (a warp reads 64 contiguous bytes per j; both halves of every 128-byte line are used by

@@ -153,6 +153,44 @@ def test_fused_finalize_exchange_on_one_device(sh, sdr_lib, world):
 
 
 @pytest.mark.gpu
+def test_exchange_error_behaviour(sdr_lib):
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        d = s.dev_alloc(4096)
+        for call in (lambda: s.split_spectrum_dev(d, 4096, 7, d), lambda: s.exchange_connect([b"x" * 64]),
+                     lambda: s.exchange_wait()):
+            with pytest.raises(sdr_lib.B200SdrError) as ei:   # nothing created / connected yet
+                call()
+            assert ei.value.status == sdr_lib.FAIL
+        for world, rank in ((0, 0), (17, 0), (4, 4)):
+            with pytest.raises(sdr_lib.B200SdrError) as ei:
+                s.exchange_create(world, rank)
+            assert ei.value.status == sdr_lib.NOT_SUPPORTED
+        s.exchange_create(1, 0)
+        with pytest.raises(sdr_lib.B200SdrError):             # already created
+            s.exchange_create(1, 0)
+        s.exchange_connect([b""])
+        for args in ((d, 4098, 7, d), (d, 4096, 0, d)):       # length not a multiple of 4 / no frames in total
+            with pytest.raises(sdr_lib.B200SdrError) as ei:
+                s.split_spectrum_dev(*args)
+            assert ei.value.status == sdr_lib.NOT_SUPPORTED
+        s.exchange_destroy()
+        s.exchange_create(1, 0)                               # can be set up again after a destroy
+        s.exchange_connect([b""])
+        s.split_spectrum_dev(d, 0, 7, d)                      # a rank without data contributes zeros
+        s.exchange_wait()
+        assert not s.to_host(d, 4096, np.float32).any()
+        s.dev_free(d)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM, avg_mode=1, ema_beta=0.1) as s:
+        s.exchange_create(1, 0)
+        s.exchange_connect([b""])
+        d = s.dev_alloc(4096)
+        with pytest.raises(sdr_lib.B200SdrError) as ei:       # EMA needs the frames in order: not splittable
+            s.split_spectrum_dev(d, 4096, 7, d)
+        assert ei.value.status == sdr_lib.NOT_SUPPORTED
+        s.dev_free(d)
+
+
+@pytest.mark.gpu
 def test_fused_exchange_times_out_instead_of_hanging(sdr_lib):
     """A peer that never arrives: the kernel's wait is bounded, exchange_wait reports FAIL."""
     import time
