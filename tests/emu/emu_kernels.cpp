@@ -107,6 +107,15 @@ int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, v
 
 int emu_sizeof_fm_state(void) { return (int)sizeof(FmState); }
 
+/* the product's spectrum launch plan (csrc/plan.h): out3 = frames, frames_per_warp, ctas_per_capture */
+void emu_plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count, uint32_t *out3)
+{
+    const b200::SpectrumPlan pl = b200::plan_spectrum(len_bytes, n_captures, sm_count);
+    out3[0] = pl.frames;
+    out3[1] = pl.frames_per_warp;
+    out3[2] = pl.ctas_per_capture;
+}
+
 /* AM over whole captures: k_am_front (optionally segmented) + k_am_back */
 int emu_am_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, uint32_t tiles_per_segment,
                  float *audio, float *env_out)

@@ -36,6 +36,29 @@ def padded(a):
     return b
 
 
+def test_spectrum_launch_plan(emu):
+    """csrc/plan.h plan_spectrum: every frame is covered exactly once, and the cost model picks long warps
+    for big batches (few partial sums), mid-sized ones for a single capture (one wave of CTAs, prologue
+    amortised) and one frame per warp for a small streaming block (all SMs busy)."""
+    emu.emu_plan_spectrum.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+
+    def plan(nbytes, ncap, sms=148):
+        out = (C.c_uint32 * 3)()
+        emu.emu_plan_spectrum(nbytes, ncap, sms, out)
+        return tuple(out)
+
+    for nbytes, ncap in ((48_000_000, 512), (48_000_000, 96), (48_000_000, 4), (48_000_000, 1), (262144, 1),
+                         (2048, 1), (2048 + 1024 * 5, 3), (4 * 262144, 7), (48_000_000, 65535)):
+        frames, fpw, ctas = plan(nbytes, ncap)
+        assert frames == (nbytes // 2 - 1024) // 512 + 1
+        assert 1 <= fpw <= 256 and (ctas - 1) * fpw * 4 < frames <= ctas * fpw * 4   # no empty CTA, all frames covered
+    assert plan(2046, 1) == (0, 0, 0)                      # shorter than one frame: nothing to launch
+    assert plan(48_000_000, 512)[1] >= 200                 # big batch: <= 60 partial sums per capture
+    assert 30 <= plan(48_000_000, 1)[1] <= 64              # one capture: ~one wave of 296 CTAs
+    assert plan(262144, 1)[1] == 1                         # one 256 KiB block: 64 CTAs of 4 single-frame warps
+    assert plan(48_000_000, 1, 74)[1] > plan(48_000_000, 1, 148)[1]   # fewer SMs -> longer warps
+
+
 @pytest.mark.parametrize("frames_per_warp,window", [(1, WIN_HANN), (3, WIN_HANN), (8, WIN_BLACKMAN)])
 def test_spectrum_kernel_logic(emu, g, frames_per_warp, window):
     n = 512 * 21 + 1024 + 100
