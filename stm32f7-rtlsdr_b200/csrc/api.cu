@@ -290,6 +290,7 @@ int stream_am(b200sdr_ctx *ctx)
     p.iq = ctx->d_stream + ctx->am_off;
     p.capture_bytes = (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
     p.q_count = n_chunks;
+    p.q_base = ctx->am_chunks;
     p.total_chunks = n_chunks;
     p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_AM_THREADS);
     p.tiles_per_segment = b200::kFmStreamTilesPerSegment; /* spread over CTAs like stream_wbfm (FIRs only: exact) */

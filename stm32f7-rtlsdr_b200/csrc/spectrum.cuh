@@ -75,7 +75,8 @@
 #define B200_SPEC_SMEM_WIN 0
 #define B200_SPEC_SMEM_TW (32 * B200_SPEC_WP * 4)
 #define B200_SPEC_SMEM_XP (B200_SPEC_SMEM_TW + 32 * 32 * 8)
-#define B200_SPEC_SMEM_BYTES (B200_SPEC_SMEM_XP + B200_SPEC_WARPS * 32 * B200_SPEC_XP * 8)
+#define B200_SPEC_SMEM_CVT (B200_SPEC_SMEM_XP + B200_SPEC_WARPS * 32 * B200_SPEC_XP * 8) /* u32 [2]: conversion constants */
+#define B200_SPEC_SMEM_BYTES (B200_SPEC_SMEM_CVT + 16)
 
 #ifdef B200_EMULATED
 #define B200_DYN_SMEM(name) unsigned char *name = EMU_DYN_SMEM
@@ -130,7 +131,10 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         s_tw[j * 32 + t] = c2_make(w.x, w.y);
 #endif
     }
+    uint32_t *s_cvt = reinterpret_cast<uint32_t *>(smem + B200_SPEC_SMEM_CVT);
+    if (tid == 0) b200_cvt_consts_store(s_cvt);
     __syncthreads();
+    const cvt_k cb = b200_cvt_consts_load(s_cvt);
 
     const uint32_t capture = blockIdx.y;
     const uint32_t warp_global = blockIdx.x * B200_SPEC_WARPS + (uint32_t)warp;
@@ -187,13 +191,13 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii) {
                 const int i = 2 * i2 + ii, e = b200_bitrev5(2 * i);
-                const c2 pa = c2_scale(c2_from_u8_lo(raw[e]), wv[2 * ii]);
+                const c2 pa = c2_scale(c2_from_u8_lo(raw[e], cb), wv[2 * ii]);
 #if B200_SPEC_FUSE_WIN
-                const c2 b = c2_from_u8_lo(raw[e + 16]);
+                const c2 b = c2_from_u8_lo(raw[e + 16], cb);
                 v[2 * i] = c2_fma_s(b, wv[2 * ii + 1], pa);
                 v[2 * i + 1] = c2_fma_s(b, -wv[2 * ii + 1], pa);
 #else
-                const c2 pb = c2_scale(c2_from_u8_lo(raw[e + 16]), wv[2 * ii + 1]);
+                const c2 pb = c2_scale(c2_from_u8_lo(raw[e + 16], cb), wv[2 * ii + 1]);
                 v[2 * i] = c2_add(pa, pb);
                 v[2 * i + 1] = c2_sub(pa, pb);
 #endif

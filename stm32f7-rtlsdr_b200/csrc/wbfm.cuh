@@ -63,7 +63,7 @@
 #define B200_FM_SM_WSUM (B200_FM_SM_E + (B200_FM_HPAD + B200_FM_TILE_OUT + 16) * 4)     /* float [8]        */
 #define B200_FM_SM_TAILC (B200_FM_SM_WSUM + 32)                                         /* c2 [2][8]        */
 #define B200_FM_SM_YLASTC (B200_FM_SM_TAILC + 2 * 8 * 8)                                /* c2 [2]           */
-#define B200_FM_SM_BAR (B200_FM_SM_YLASTC + 16)                                         /* u64              */
+#define B200_FM_SM_BAR (B200_FM_SM_YLASTC + 16)                                         /* u64, u32 [2]     */
 #define B200_FM_SMEM_BYTES (B200_FM_SM_BAR + 16)
 
 #ifndef B200_DYN_SMEM
@@ -85,6 +85,9 @@ struct FmState {
 
 struct FmTaps {
     float h1[B200_FM_T1]; /* stage 1, includes 1/127.5                         */
+    float h1s[B200_FM_T1]; /* h1 * 2^133: multiplies the raw-byte floats u * 2^-133 (cplx2.cuh form C) */
+    float bias_full;       /* -127.5 sum_k h1[k]: start value of an accumulator (form C)               */
+    float bias_head[8];    /* -127.5 sum_{k <= 10 i} h1[k]: outputs 0..7 of a stream (x[n < 0] = 0)    */
     float h2[B200_FM_T2]; /* stage 2, includes the audio gain                  */
     float apow[16];       /* a^(i+1), i = 0..11, a = 1 - alpha                 */
     float alpha;
@@ -115,7 +118,7 @@ struct FmParams {
 
 /* one input sample scattered into its (up to) 8 outputs; J is the sample index in the chunk */
 template <int J>
-B200_DEV void b200_fm_scatter(c2 x, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
+B200_DEV void b200_fm_scatter(c2 x, c2 acc0, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
 {
 #pragma unroll
     for (int i = (J + 9) / 10; i <= (J + 79) / 10; ++i) {
@@ -124,29 +127,29 @@ B200_DEV void b200_fm_scatter(c2 x, const float (&h)[40], c2 (&acc)[8], c2 (&hea
     }
     if (J % 10 == 0 && J / 10 < B200_FM_OPT) {
         head[J / 10] = acc[(J / 10) & 7];
-        acc[(J / 10) & 7] = c2_zero();
+        acc[(J / 10) & 7] = acc0; /* output J/10 + 8 starts here: zero, or its share of the -127.5 offset */
     }
 }
 
 template <int Q>
 struct b200_fm_words {
-    B200_DEVM static void run(const uint4 *raw, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
+    B200_DEVM static void run(const uint4 *raw, cvt_k cb, c2 acc0, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
     {
         const uint4 r = raw[Q];
-        b200_fm_scatter<8 * Q + 0>(c2_from_u8_lo(r.x), h, acc, head);
-        b200_fm_scatter<8 * Q + 1>(c2_from_u8_hi(r.x), h, acc, head);
-        b200_fm_scatter<8 * Q + 2>(c2_from_u8_lo(r.y), h, acc, head);
-        b200_fm_scatter<8 * Q + 3>(c2_from_u8_hi(r.y), h, acc, head);
-        b200_fm_scatter<8 * Q + 4>(c2_from_u8_lo(r.z), h, acc, head);
-        b200_fm_scatter<8 * Q + 5>(c2_from_u8_hi(r.z), h, acc, head);
-        b200_fm_scatter<8 * Q + 6>(c2_from_u8_lo(r.w), h, acc, head);
-        b200_fm_scatter<8 * Q + 7>(c2_from_u8_hi(r.w), h, acc, head);
-        b200_fm_words<Q + 1>::run(raw, h, acc, head);
+        b200_fm_scatter<8 * Q + 0>(B200_FIR_X_LO(r.x, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 1>(B200_FIR_X_HI(r.x, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 2>(B200_FIR_X_LO(r.y, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 3>(B200_FIR_X_HI(r.y, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 4>(B200_FIR_X_LO(r.z, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 5>(B200_FIR_X_HI(r.z, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 6>(B200_FIR_X_LO(r.w, cb), acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 7>(B200_FIR_X_HI(r.w, cb), acc0, h, acc, head);
+        b200_fm_words<Q + 1>::run(raw, cb, acc0, h, acc, head);
     }
 };
 template <>
 struct b200_fm_words<B200_FM_CHUNK / 8> {
-    B200_DEVM static void run(const uint4 *, const float (&)[40], c2 (&)[8], c2 (&)[B200_FM_OPT]) {}
+    B200_DEVM static void run(const uint4 *, cvt_k, c2, const float (&)[40], c2 (&)[8], c2 (&)[B200_FM_OPT]) {}
 };
 
 #ifdef B200_EMULATED
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
     c2 *s_tailc = reinterpret_cast<c2 *>(smem + B200_FM_SM_TAILC);
     c2 *s_ylastc = reinterpret_cast<c2 *>(smem + B200_FM_SM_YLASTC);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + B200_FM_SM_BAR);
+    uint32_t *s_cvt = reinterpret_cast<uint32_t *>(smem + B200_FM_SM_BAR + 8); /* conversion constants (cplx2.cuh) */
 
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t capture = blockIdx.y;
@@ -217,7 +221,13 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
     /* taps and scan constants -> registers */
     float h[40];
 #pragma unroll
+#if B200_FIR_RAWU8
+    for (int k = 0; k < 40; ++k) h[k] = taps->h1s[k];
+    const c2 acc0 = c2_make(taps->bias_full, taps->bias_full);
+#else
     for (int k = 0; k < 40; ++k) h[k] = taps->h1[k];
+    const c2 acc0 = c2_zero();
+#endif
     const float alpha = taps->alpha;
     const float a1 = 1.0f - alpha;
     float lane_pow = 1.0f; /* (a^12)^lane */
@@ -229,6 +239,10 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
     if (tid < 8) {
         float tr = 0.0f, ti = 0.0f;
         if (st_in) { tr = st_in->tail[2 * tid]; ti = st_in->tail[2 * tid + 1]; }
+#if B200_FIR_RAWU8
+        /* first outputs of a capture / stream: only the taps that reach samples n >= 0 carry the offset */
+        if (seg == 0 && p.m_base == 0) tr = ti = taps->bias_head[tid];
+#endif
         s_tailc[8 + tid] = c2_make(tr, ti); /* tile 0 reads carry buffer 1 */
     }
     if (tid == 8) {
@@ -253,8 +267,10 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         b200_mbar_init(s_bar, 1);
         b200_mbar_fence_init();
         if (my_tiles > 0) issue_tile(0);
+        b200_cvt_consts_store(s_cvt);
     }
     __syncthreads();
+    const cvt_k cb = b200_cvt_consts_load(s_cvt);
 
     for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint32_t tile = t_begin + it;
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = c2_zero();
         const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_FM_SM_RAW + tid * (2 * B200_FM_CHUNK));
-        b200_fm_words<0>::run(raw, h, acc, head);
+        b200_fm_words<0>::run(raw, cb, acc0, h, acc, head);
         /* tails: outputs 12..19 live in acc[i & 7] -> next thread's heads 0..7.
          * exchange tile is [i][thread] so a warp's stores / loads are contiguous */
         if (tid == last) {

@@ -163,6 +163,7 @@ int emu_am_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, voi
     p.iq = iq;
     p.capture_bytes = (uint64_t)n_chunks * 2 * B200_AM_CHUNK;
     p.q_count = n_chunks;
+    p.q_base = chunk_base;
     p.total_chunks = n_chunks;
     p.n_tiles = (uint32_t)b200::ceil_div(n_chunks, B200_AM_THREADS);
     p.tiles_per_segment = tiles_per_segment ? tiles_per_segment : (p.n_tiles ? p.n_tiles : 1); /* 0: one segment */

@@ -14,7 +14,7 @@ import json, sys
 try:
     d=json.loads(open('gpurun_out/bench_var.txt').read().strip().splitlines()[-1])
     c=d['chains']
-    print(f"{sys.argv[1]:70s} value {d['value']:9.0f}  spec {c['spectrum']['MSps_per_gpu']:9.0f} ({c['spectrum']['hbm_frac']:.4f})  wbfm {c['wbfm']['MSps_per_gpu']:9.0f} ({c['wbfm']['hbm_frac']:.4f})")
+    print(f"{sys.argv[1]:70s} value {d['value']:9.0f}  spec {c['spectrum']['MSps_per_gpu']:9.0f} ({c['spectrum']['hbm_frac']:.4f})  wbfm {c['wbfm']['MSps_per_gpu']:9.0f} ({c['wbfm']['hbm_frac']:.4f})  am {c.get('am',{}).get('MSps_per_gpu',0):9.0f} ({c.get('am',{}).get('hbm_frac',0):.4f})")
 except Exception as e:
     print(sys.argv[1], 'FAILED', e, open('gpurun_out/bench_var.txt').read()[-500:])
 PY

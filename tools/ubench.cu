@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(512) k(float *out, long long *cyc, float seed)
     uint32_t w = threadIdx.x * 2654435761u, acc32 = 0;
     uint32_t iv[8];
     for (int i = 0; i < 8; ++i) iv[i] = w + i;
+    const u64 pden = pk(__uint_as_float(0x00110000u + (threadIdx.x << 16 & 0x7f0000u)), __uint_as_float(0x00350000u)), pbig = pk(1e30f, -1e30f);
+    const uint32_t hv = 0x3c003c00u + (threadIdx.x & 3); /* two f16 values ~1 */
     __shared__ u64 sm[1024];
     sm[threadIdx.x] = px; sm[threadIdx.x + 512] = py;
     for (int i = 0; i < 8; ++i) { a[i] = i * 0.1f; p[i] = pk(i * 0.1f, i * 0.2f); }
@@ -136,6 +138,39 @@ __global__ void __launch_bounds__(512) k(float *out, long long *cyc, float seed)
                 asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
                 iv[i] = __float_as_uint(f) + iv[i];
             }
+        } else if (MODE == 24) { // FHADD x8 independent (f32 = f16 half of a register + f32), sm_100 mixed-precision add
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, hi, %0; }" : "+f"(a[i]) : "r"(hv));
+        } else if (MODE == 25) { // FFMA2 + FHADD 1:1
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                asm volatile("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, hi, %0; }" : "+f"(a[i]) : "r"(hv));
+            }
+        } else if (MODE == 26) { // conversion form A next to the FIR: 2 PRMT + FADD2 + 8 FFMA2
+            asm volatile("prmt.b32 %0, %0, %1, 0x7504;" : "+r"(iv[0]) : "r"(w));
+            asm volatile("prmt.b32 %0, %0, %1, 0x7514;" : "+r"(iv[1]) : "r"(w));
+            asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[0]) : "l"(px));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+        } else if (MODE == 27) { // conversion form B next to the FIR: PRMT + 2 FHADD + 8 FFMA2
+            asm volatile("prmt.b32 %0, %0, %1, 0x4140;" : "+r"(iv[0]) : "r"(w));
+            asm volatile("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, lo, %0; }" : "+f"(a[0]) : "r"(hv));
+            asm volatile("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, hi, %0; }" : "+f"(a[1]) : "r"(hv));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+        } else if (MODE == 30) { // FFMA2 whose multiplicand is a pair of SUBNORMAL floats (u8 raw form, cplx2.cuh form C)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(pden), "l"(pbig));
+        } else if (MODE == 28) { // HFMA2 (f16x2) x8 independent: is the half pipe the FP32 pipe?
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(iv[i]) : "r"(hv), "r"(w));
+        } else if (MODE == 29) { // FFMA2 + HFMA2 1:1
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p[i]) : "l"(px), "l"(py));
+                asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(iv[i]) : "r"(hv), "r"(w));
+            }
         } else if (MODE == 20) { // FFMA2 + LDS.32 conflict-free 2:1
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -198,5 +233,12 @@ int main()
     run<21>("IADD + I2F.U8 + FADD (x8)", 24, 0);
     run<22>("IADD + FADD (x8) baseline", 16, 0);
     run<23>("I2F.U8 + FFMA2 + IADD (x8)", 24, 0);
+    run<24>("FHADD x8 indep", 8, 1);
+    run<25>("FFMA2 + FHADD 1:1", 16, 1.5);
+    run<26>("cvt A: 2 PRMT + FADD2 + 8 FFMA2", 11, 18.0 / 11);
+    run<27>("cvt B: PRMT + 2 FHADD + 8 FFMA2", 11, 18.0 / 11);
+    run<30>("FFMA2 subnormal multiplicand", 8, 2);
+    run<28>("HFMA2 x8 indep", 8, 0);
+    run<29>("FFMA2 + HFMA2 1:1", 16, 1);
     return 0;
 }

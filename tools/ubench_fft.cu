@@ -25,12 +25,15 @@ __global__ void __launch_bounds__(128, MINB) k_fft(float *out, const uint32_t *w
         v[i] = c2_make(1e-3f * (float)(threadIdx.x + i), 2e-3f * (float)i);
         w[i] = words[(threadIdx.x + i) & 1023];
     }
+    __shared__ uint32_t s_cvt[2];
+    if (threadIdx.x == 0) b200_cvt_consts_store(s_cvt);
     __syncthreads();
+    const cvt_k cb = b200_cvt_consts_load(s_cvt);
     for (int it = 0; it < iters; ++it) {
         if (MODE & 1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                v[i] = c2_add(v[i], c2_from_u8_lo(w[i]));
+                v[i] = c2_add(v[i], c2_from_u8_lo(w[i], cb));
                 w[i] += 0x0101u; /* keep the conversion loop-variant (one IADD per word) */
             }
         }
