@@ -147,3 +147,32 @@ class RefHost:
 
 def wrap_phase(a):
     return (np.asarray(a) + np.pi) % (2 * np.pi) - np.pi
+
+
+def extreme_patterns(nb):
+    """byte patterns that stress the raw-byte FIR form (cplx2.cuh form C).  Constant ones (AM only: a
+    constant input puts the FM discriminator on its branch cut): the largest offsets the accumulators ever
+    cancel (all 0 / all 255), the smallest signal a u8 stream can carry (127 / 128: u - 127.5 = -+0.5), both
+    halves of the subnormal / normal split side by side, a full-scale square wave.  Rotating ones (FM and
+    AM): a full-scale tone (bytes 0 and 255 occur), the smallest rotating phasor a u8 stream can carry
+    (I, Q in {127, 128}), and a small tone on top of a large DC offset."""
+    n = nb // 2
+    const, rot = {}, {}
+    for name, (a, b) in {"all0": (0, 0), "all255": (255, 255), "half_lsb": (127, 128), "split": (127, 255)}.items():
+        v = np.empty(nb, np.uint8)
+        v[0::2], v[1::2] = a, b
+        const[name] = v
+    sq = np.zeros(nb, np.uint8)
+    sq[(np.arange(nb) // 14) % 2 == 0] = 255
+    const["square"] = sq
+    ph = 2 * np.pi * 50e3 / 2.4e6 * np.arange(n)
+    def pack(i, q):
+        v = np.empty(nb, np.uint8)
+        v[0::2], v[1::2] = np.clip(np.rint(i), 0, 255), np.clip(np.rint(q), 0, 255)
+        return v
+    rot["fullscale_tone"] = pack(127.5 + 127.5 * np.cos(ph), 127.5 + 127.5 * np.sin(ph))
+    rot["half_lsb_rotation"] = pack(127.5 + 0.5 * np.sign(np.cos(ph + 0.3)), 127.5 + 0.5 * np.sign(np.sin(ph + 0.3)))
+    rot["tone_on_dc"] = pack(227.5 + 20 * np.cos(ph), 27.5 + 20 * np.sin(ph))
+    return const, rot
+
+

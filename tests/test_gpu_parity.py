@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle_api import (AVG_EMA, SYNTH_AM, SYNTH_COUNTER, SYNTH_MULTITONE, SYNTH_WBFM, WIN_BLACKMAN, WIN_HANN,
-                        WIN_RECT, Golden, RefHost, wrap_phase)
+                        WIN_RECT, Golden, RefHost, wrap_phase, extreme_patterns)
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -194,6 +194,22 @@ def test_wbfm_batches(sdr, g, n_captures, len_each):
         assert audio[c].size == ga.size and disc[c].size == gd.size
         assert np.max(np.abs(wrap_phase(disc[c] - gd))) <= DISC_ATOL
         assert np.max(np.abs(audio[c] - ga)) <= FM_AUDIO_ATOL
+
+
+@pytest.mark.parametrize("name", ["all0", "all255", "half_lsb", "split", "square", "fullscale_tone", "half_lsb_rotation", "tone_on_dc"])
+def test_fir_chains_extreme_bytes(sdr, g, name):
+    """The FIR kernels read the bytes as raw (sub)normal floats and cancel the -127.5 offset in the accumulators
+    (cplx2.cuh form C): largest offsets, smallest possible signals, both halves of the subnormal / normal split."""
+    nb = 2 * (30720 * 3 + 1208)
+    const, rot = extreme_patterns(nb)
+    iq = rot[name] if name in rot else const[name]
+    if name in rot:  # a constant input sits on the discriminator's branch cut: FM only for the rotating patterns
+        audio, disc = sdr.wbfm(iq, 1, want_disc=True)
+        ga, gd = g.wbfm(iq, want_disc=True)
+        # the first outputs see the filter's rise from x[n < 0] = 0, where |y| passes through ~0
+        assert np.max(np.abs(wrap_phase(disc[0] - gd))[16:]) <= DISC_ATOL
+        assert np.max(np.abs(audio[0] - ga)[8:]) <= FM_AUDIO_ATOL
+    assert np.max(np.abs(sdr.am(iq, 1)[0] - g.am(iq))) <= 2 * AM_AUDIO_ATOL
 
 
 def test_wbfm_host_path_equals_device_path(sdr, g):
