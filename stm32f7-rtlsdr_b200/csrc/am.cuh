@@ -68,8 +68,8 @@ struct AmBackState {
 struct AmTaps {
     float g1[B200_AM_T1];
     float g1s[B200_AM_T1]; /* g1 * 2^133 (cplx2.cuh form C) */
-    float bias_full;       /* -127.5 sum_k g1[k]            */
-    float bias_head[4];    /* -127.5 sum_{k <= 20 i} g1[k]  */
+    float bias_half;       /* -127.5 sum_k g1[k] / 2 (FmTaps::bias_half)            */
+    float bias_head[4];    /* -127.5 sum_{k <= 20 i} g1[k] (FmTaps::bias_head)       */
     float g2[B200_AM_T2];
     float g3[B200_AM_T3];
     float rho;
@@ -106,8 +106,12 @@ B200_DEV void b200_am_scatter(c2 x, c2 acc0, const float (&g)[40], c2 (&acc)[4],
         acc[i & 3] = c2_fma_s(x, g[k < 40 ? k : 79 - k], acc[i & 3]);
     }
     if (J % 20 == 0 && J / 20 < B200_AM_OPT) {
+#if B200_FIR_RAWU8
+        head[J / 20] = (J / 20 >= 4) ? c2_add(acc[(J / 20) & 3], acc0) : acc[(J / 20) & 3]; /* see wbfm.cuh */
+#else
         head[J / 20] = acc[(J / 20) & 3];
-        acc[(J / 20) & 3] = acc0; /* output J/20 + 4 starts here (wbfm.cuh) */
+#endif
+        acc[(J / 20) & 3] = acc0; /* output J/20 + 4 starts here */
     }
 }
 template <int Q>
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
 #pragma unroll
 #if B200_FIR_RAWU8
     for (int k = 0; k < 40; ++k) g[k] = taps->g1s[k];
-    const c2 acc0 = c2_make(taps->bias_full, taps->bias_full);
+    const c2 acc0 = c2_make(taps->bias_half, taps->bias_half);
 #else
     for (int k = 0; k < 40; ++k) g[k] = taps->g1[k];
     const c2 acc0 = c2_zero();
@@ -205,8 +209,9 @@ __global__ void __launch_bounds__(B200_AM_THREADS, 3) k_am_front(AmFrontParams p
 
         b200_mbar_wait(s_bar, it & 1);
         c2 acc[4], head[B200_AM_OPT];
+        const c2 start = (tid == 0 && it == 0 && seg == 0 && p.q_base == 0) ? c2_zero() : acc0; /* wbfm.cuh */
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = c2_zero();
+        for (int i = 0; i < 4; ++i) acc[i] = start;
         const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_AM_SM_RAW + tid * (2 * B200_AM_CHUNK));
         b200_am_words<0>::run(raw, cb, acc0, g, acc, head);
         if (tid == last) {

@@ -86,13 +86,17 @@ inline void fill_fm_taps(FmTaps &t)
     for (int k = 0; k < B200_FM_T1; ++k) t.h1[k] = (float)h1[k];
     /* raw-byte form of the FIR (cplx2.cuh form C): taps x 2^133, and the -127.5 offset summed over the
      * float taps actually used, so the constant part of the input cancels to rounding */
-    double run = 0.0;
+    double total = 0.0, run = 0.0;
     for (int k = 0; k < B200_FM_T1; ++k) {
         t.h1s[k] = (float)std::ldexp((double)t.h1[k], B200_U8RAW_LOG2);
+        total += (double)t.h1[k];
+    }
+    t.bias_half = (float)(-127.5 * total / 2);
+    /* output i of a stream sees real samples through taps k <= 10 i only */
+    for (int k = 0; k < B200_FM_T1; ++k) {
         run += (double)t.h1[k];
         if (k % 10 == 0 && k / 10 < 8) t.bias_head[k / 10] = (float)(-127.5 * run);
     }
-    t.bias_full = (float)(-127.5 * run);
     for (int k = 0; k < B200_FM_T2; ++k) t.h2[k] = (float)h2[k];
     const double alpha = deemph_alpha(), a = 1.0 - alpha;
     t.alpha = (float)alpha;
@@ -129,13 +133,16 @@ inline void fill_am_taps(AmTaps &t)
 {
     const std::vector<double> g1 = design_taps(2), g2 = design_taps(3), g3 = design_taps(4);
     for (int k = 0; k < B200_AM_T1; ++k) t.g1[k] = (float)g1[k];
-    double run = 0.0;
+    double total = 0.0, run = 0.0;
     for (int k = 0; k < B200_AM_T1; ++k) { /* see fill_fm_taps */
         t.g1s[k] = (float)std::ldexp((double)t.g1[k], B200_U8RAW_LOG2);
+        total += (double)t.g1[k];
+    }
+    t.bias_half = (float)(-127.5 * total / 2);
+    for (int k = 0; k < B200_AM_T1; ++k) {
         run += (double)t.g1[k];
         if (k % 20 == 0 && k / 20 < 4) t.bias_head[k / 20] = (float)(-127.5 * run);
     }
-    t.bias_full = (float)(-127.5 * run);
     for (int k = 0; k < B200_AM_T2; ++k) t.g2[k] = (float)g2[k];
     for (int k = 0; k < B200_AM_T3; ++k) t.g3[k] = (float)g3[k];
     const double rho = dcblock_rho(), rho4 = std::pow(rho, B200_AMB_PER);

@@ -86,8 +86,12 @@ struct FmState {
 struct FmTaps {
     float h1[B200_FM_T1]; /* stage 1, includes 1/127.5                         */
     float h1s[B200_FM_T1]; /* h1 * 2^133: multiplies the raw-byte floats u * 2^-133 (cplx2.cuh form C) */
-    float bias_full;       /* -127.5 sum_k h1[k]: start value of an accumulator (form C)               */
-    float bias_head[8];    /* -127.5 sum_{k <= 10 i} h1[k]: outputs 0..7 of a stream (x[n < 0] = 0)    */
+    float bias_half;       /* -127.5 sum_k h1[k] / 2: start value of EVERY accumulator (form C).  An output that
+                              straddles two threads collects one half in each; one that completes inside a thread
+                              gets the second half when it is taken out.  Starting at half the offset keeps the
+                              partial sums in [-0.5, 0.5] of full scale instead of [-1, 0]: half the rounding error */
+    float bias_head[8];    /* -127.5 sum_{k <= 10 i} h1[k]: carried-in part of outputs 0..7 of a stream, whose
+                              own part starts from zero (x[n < 0] = 0; small and exact)                       */
     float h2[B200_FM_T2]; /* stage 2, includes the audio gain                  */
     float apow[16];       /* a^(i+1), i = 0..11, a = 1 - alpha                 */
     float alpha;
@@ -126,8 +130,13 @@ B200_DEV void b200_fm_scatter(c2 x, c2 acc0, const float (&h)[40], c2 (&acc)[8],
         acc[i & 7] = c2_fma_s(x, h[k < 40 ? k : 79 - k], acc[i & 7]);
     }
     if (J % 10 == 0 && J / 10 < B200_FM_OPT) {
+#if B200_FIR_RAWU8
+        /* outputs 8..11 lived in this thread only: they hold one half of the offset, add the other */
+        head[J / 10] = (J / 10 >= 8) ? c2_add(acc[(J / 10) & 7], acc0) : acc[(J / 10) & 7];
+#else
         head[J / 10] = acc[(J / 10) & 7];
-        acc[(J / 10) & 7] = acc0; /* output J/10 + 8 starts here: zero, or its share of the -127.5 offset */
+#endif
+        acc[(J / 10) & 7] = acc0; /* output J/10 + 8 starts here: zero, or half of the -127.5 offset */
     }
 }
 
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
 #pragma unroll
 #if B200_FIR_RAWU8
     for (int k = 0; k < 40; ++k) h[k] = taps->h1s[k];
-    const c2 acc0 = c2_make(taps->bias_full, taps->bias_full);
+    const c2 acc0 = c2_make(taps->bias_half, taps->bias_half);
 #else
     for (int k = 0; k < 40; ++k) h[k] = taps->h1[k];
     const c2 acc0 = c2_zero();
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         float tr = 0.0f, ti = 0.0f;
         if (st_in) { tr = st_in->tail[2 * tid]; ti = st_in->tail[2 * tid + 1]; }
 #if B200_FIR_RAWU8
-        /* first outputs of a capture / stream: only the taps that reach samples n >= 0 carry the offset */
+        /* first outputs of a capture / stream: x[n < 0] = 0 */
         if (seg == 0 && p.m_base == 0) tr = ti = taps->bias_head[tid];
 #endif
         s_tailc[8 + tid] = c2_make(tr, ti); /* tile 0 reads carry buffer 1 */
@@ -284,8 +293,12 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         /* ---- stage 1: scatter FIR over this thread's 120 samples ---- */
         b200_mbar_wait(s_bar, it & 1);
         c2 acc[8], head[B200_FM_OPT];
+        /* the very first chunk of a capture / stream: its outputs 0..7 are the filter's rise from nothing
+         * (|y[0]| ~ 1e-6 of full scale) and are kept exact -- own part from zero, carried-in part = the small
+         * exact offset of the taps that reach n >= 0 (bias_head) -- instead of two halves of O(0.5) */
+        const c2 start = (tid == 0 && it == 0 && seg == 0 && p.m_base == 0) ? c2_zero() : acc0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = c2_zero();
+        for (int i = 0; i < 8; ++i) acc[i] = start;
         const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_FM_SM_RAW + tid * (2 * B200_FM_CHUNK));
         b200_fm_words<0>::run(raw, cb, acc0, h, acc, head);
         /* tails: outputs 12..19 live in acc[i & 7] -> next thread's heads 0..7.
