@@ -546,6 +546,15 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
         AmTaps at{};
         b200::fill_am_taps(at);
         CK(cudaMemcpyToSymbol(c_am_taps, &at, sizeof at));
+        /* the raw-byte FIR form (cplx2.cuh form C) multiplies by tap * 2^133: must stay finite */
+        bool scaled_ok = true;
+        for (float v : ft.h1s) scaled_ok = scaled_ok && std::isfinite(v);
+        for (float v : at.g1s) scaled_ok = scaled_ok && std::isfinite(v);
+        if (!scaled_ok) {
+            fprintf(stderr, "b200sdr_create: a stage-1 FIR tap overflows when scaled by 2^%d\n", B200_U8RAW_LOG2);
+            b200sdr_destroy(ctx);
+            return B200SDR_FAIL;
+        }
         for (unsigned t = 0; t < 5; ++t) {
             std::vector<double> h = b200::design_taps(t);
             ctx->h_taps[t].assign(h.begin(), h.end());
