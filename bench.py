@@ -452,14 +452,16 @@ def main():
                          "frac_of_fp32_ceiling": spec_gbs / (2.0 * 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * 512 / 1028 / 1e9)},
             "chains": {
                 "spectrum": {"ms_per_step": ms_spec / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_spec * 1e-3) / 1e6,
-                             "GBps": spec_gbs, "hbm_frac": spec_gbs / hbm_peak},
+                             "GBps": spec_gbs, "hbm_frac": spec_gbs / hbm_peak, "hbm_frac_nominal_8TBps": spec_gbs / 8000.0},
                 "wbfm": {"ms_per_step": ms_fm / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_fm * 1e-3) / 1e6,
-                         "GBps": fm_gbs, "hbm_frac": fm_gbs / hbm_peak, "algorithmic_bytes_per_sample": fm_bytes},
+                         "GBps": fm_gbs, "hbm_frac": fm_gbs / hbm_peak, "hbm_frac_nominal_8TBps": fm_gbs / 8000.0,
+                         "algorithmic_bytes_per_sample": fm_bytes},
                 "convert_cf32": {"ms_per_step": ms_conv / args.steps, "MSps_per_gpu": Bc * CAPTURE_SAMPLES * args.steps / (ms_conv * 1e-3) / 1e6,
                                  "GBps": conv_gbs, "hbm_frac": conv_gbs / hbm_peak, "algorithmic_bytes_per_sample": 10.0,
                                  "note": "K2 alone over %d captures: HBM-bound reference, not part of `value`" % Bc},
                 "am": {"ms_per_step": ms_am / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e6,
-                       "GBps": am_gbs, "hbm_frac": am_gbs / hbm_peak, "algorithmic_bytes_per_sample": am_bytes,
+                       "GBps": am_gbs, "hbm_frac": am_gbs / hbm_peak, "hbm_frac_nominal_8TBps": am_gbs / 8000.0,
+                       "algorithmic_bytes_per_sample": am_bytes,
                        "note": "config[3], secondary; not part of `value`"},
             },
             "ingest": ingest,
