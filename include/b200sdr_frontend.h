@@ -10,6 +10,7 @@
  *   b200sdr_rtl_fir_pack      RTLSDR_set_fir,         RTL/Src/usbh_rtlsdr.c:534-575
  *   b200sdr_rtl_default_fir   RTLSDR_FIR table,       RTL/Inc/usbh_rtlsdr.h:340-345
  *   b200sdr_e4k_pll_params    E4K_compute_pll_params, RTL/Src/tuner_e4k.c:689-737 (+ :301-361)
+ *   b200sdr_rtl_init_sequence USBH_RTLSDR_ClassRequest, RTL/Src/usbh_rtlsdr.c:809-945 (the register writes as data)
  */
 #ifndef B200SDR_FRONTEND_H
 #define B200SDR_FRONTEND_H
@@ -40,6 +41,40 @@ B200SDR_API void b200sdr_rtl_default_fir(int32_t coeff[16]);
 /* Pack 16 coefficients into the 20 bytes written to the demod FIR registers.
  * B200SDR_NOT_SUPPORTED if a coefficient is out of range (bytes are still produced). */
 B200SDR_API int32_t b200sdr_rtl_fir_pack(const int32_t coeff[16], uint8_t out20[20]);
+
+/* One USB control transfer of the RTL2832 bring-up, exactly as the firmware puts it on the wire: the setup
+ * packet (vendor request 0; RTLSDR_write_reg / RTLSDR_demod_write_reg / RTLSDR_demod_read_reg /
+ * RTLSDR_write_array / RTLSDR_read_array, RTL/Src/usbh_rtlsdr.c:262-345, :445-521) and, for OUT transfers, the
+ * wLength payload bytes.  `step` is the firmware's request number (case labels of usbh_rtlsdr.c:826-907). */
+typedef struct b200sdr_ctl_xfer {
+    uint8_t  bmRequestType; /* 0x40 vendor OUT, 0xC0 vendor IN (CTRL_OUT / CTRL_IN, RTL/Inc/usbh_rtlsdr.h:357-358) */
+    uint8_t  bRequest;      /* always 0 */
+    uint16_t wValue;        /* register address; demod: (addr << 8) | 0x20; I2C: the chip's bus address */
+    uint16_t wIndex;        /* (block << 8) | 0x10 for writes, (block << 8) for reads; demod: page | 0x10, reads page 0x0a */
+    uint16_t wLength;       /* 1 or 2 */
+    uint8_t  data[2];       /* OUT payload (16-bit values travel high byte first); zero for IN */
+    uint8_t  step;          /* 0..33 */
+    uint8_t  reserved;
+} b200sdr_ctl_xfer;
+
+#define B200SDR_RTL_INIT_TEST_MODE 1u /* flags: step 31 switches the counter test pattern ON, as the firmware does
+                                         (usbh_rtlsdr.c:901); without it the demodulator output is selected */
+
+/* The complete control-transfer sequence USBH_RTLSDR_ClassRequest issues between enumeration and the first bulk
+ * read, as data: USB block and demodulator power-up (steps 0-5), soft reset, spectrum inversion / DDC / IF
+ * registers (6-15), the 20 FIR bytes (16, from `fir16`, NULL = the firmware's table), SDR mode, AGC / PID / ADC /
+ * zero-IF setup (17-25), I2C repeater (26), the E4000 probe read (27), the resampler ratio for `samp_rate` with the
+ * two soft resets around it (30, RTLSDR_set_sample_rate states 1-9), test mode (31) and the two EPA FIFO resets
+ * (32-33).  Every demodulator write is followed by the firmware's dummy read of page 0x0a register 0x01.  The
+ * tuner's own initialisation (steps 28, 29 and SetBW inside step 30) belongs to the tuner driver and is not part
+ * of the list.  With samp_rate = 240000, the default FIR and B200SDR_RTL_INIT_TEST_MODE the list is transfer for
+ * transfer what the reference firmware emits (108 transfers; tests/test_frontend_parity.py records the
+ * reference's own FSM in oracle A).
+ * Writes min(capacity, n) entries, *n_out = n.  B200SDR_OK; B200SDR_NOT_SUPPORTED for a rate the resampler cannot
+ * produce or a FIR coefficient out of range (the list is still produced, like the firmware would);
+ * B200SDR_BUSY if capacity < n; B200SDR_FAIL for null pointers / zero rate. */
+B200SDR_API int32_t b200sdr_rtl_init_sequence(uint32_t samp_rate, uint32_t xtal_hz, const int32_t *fir16, uint32_t flags,
+                                              b200sdr_ctl_xfer *out, uint32_t capacity, uint32_t *n_out);
 
 typedef struct b200sdr_e4k_pll {
     uint32_t fosc, intended_flo, flo; /* flo = frequency actually synthesised */

@@ -111,9 +111,43 @@ USBH_StatusTypeDef USBH_OpenPipe(USBH_HandleTypeDef *phost, uint8_t pipe_num, ui
     HAL_HCD_HC_Init((HCD_HandleTypeDef *)phost->pData, pipe_num, epnum, dev_address, speed, ep_type, mps);
     return USBH_OK;
 }
+/* Control transfers complete at once.  While a trace is being recorded (section 5) every transfer is
+ * logged as the setup packet the reference put into phost->Control.setup plus its payload; IN transfers are
+ * answered by a two-line device model: an I2C read through the repeater returns the E4000's chip id when
+ * register E4K_CHECK_ADDR of E4K_I2C_ADDR was addressed last (so the reference's own probe finds a tuner,
+ * usbh_rtlsdr.c:961-975), everything else reads 0. */
+struct ref_ctl_rec { uint8_t bmRequestType, bRequest; uint16_t wValue, wIndex, wLength; uint8_t data[2]; uint8_t step, pad; };
+static struct ref_ctl_rec *g_trace;
+static uint32_t g_trace_cap, g_trace_n;
+static uint16_t g_i2c_last_addr;
+static uint8_t g_i2c_last_reg;
+static uint8_t ref_trace_step(void);
 USBH_StatusTypeDef USBH_CtlReq(USBH_HandleTypeDef *phost, uint8_t *buff, uint16_t length)
 {
-    (void)phost; (void)buff; (void)length;
+    if (!g_trace) return USBH_OK;
+    const USB_Setup_TypeDef *su = &phost->Control.setup;
+    const int in = (su->b.bmRequestType & 0x80) != 0;
+    if (in) {
+        memset(buff, 0, length);
+        if (su->b.wIndex.w == (IICB << 8) && su->b.wValue.w == E4K_I2C_ADDR && g_i2c_last_addr == E4K_I2C_ADDR &&
+            g_i2c_last_reg == E4K_CHECK_ADDR && length >= 1)
+            buff[0] = E4K_CHECK_VAL;
+    } else if (su->b.wIndex.w == ((IICB << 8) | 0x10) && length >= 1) {
+        g_i2c_last_addr = su->b.wValue.w;
+        g_i2c_last_reg = buff[0];
+    }
+    if (g_trace_n < g_trace_cap) {
+        struct ref_ctl_rec *r = &g_trace[g_trace_n];
+        memset(r, 0, sizeof *r);
+        r->bmRequestType = su->b.bmRequestType;
+        r->bRequest = su->b.bRequest;
+        r->wValue = su->b.wValue.w;
+        r->wIndex = su->b.wIndex.w;
+        r->wLength = su->b.wLength.w;
+        if (!in) memcpy(r->data, buff, length < 2 ? length : 2);
+        r->step = ref_trace_step();
+    }
+    g_trace_n++;
     return USBH_OK;
 }
 USBH_StatusTypeDef USBH_Process(USBH_HandleTypeDef *phost) { (void)phost; return USBH_OK; }
@@ -329,9 +363,60 @@ uint32_t ref_e4k_pll(uint32_t fosc, uint32_t intended_flo, uint32_t out8[8])
     return flo;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * 5. the register-initialisation sequence (section 8f row 2, "register sequences as data"): the reference's
+ * own, unmodified USBH_RTLSDR_ClassRequest (usbh_rtlsdr.c:809-945), reached through the class vtable as
+ * USBH_Process does (usbh_core.c:557), polled until it reports the class active.  Every control transfer it
+ * issues is recorded by USBH_CtlReq above.  The E4000 driver's own init (steps 28, 29 and the SetBW call
+ * inside RTLSDR_set_sample_rate) is a separate state machine over dozens of I2C registers; it is replaced by
+ * a tuner that accepts everything, after the reference's probe has found "its" E4000.
+ * Returns the number of transfers (which may exceed cap), or < 0.
+ * ------------------------------------------------------------------------------------------- */
+static USBH_StatusTypeDef tuner_ok(USBH_HandleTypeDef *phost) { (void)phost; return USBH_OK; }
+static RTLSDR_TunerTypeDef g_null_tuner;
+static void user_cb(USBH_HandleTypeDef *phost, uint8_t id) { (void)phost; (void)id; }
+static uint8_t ref_trace_step(void) { return handle()->reqNumber; }
+
+long ref_init_trace(uint8_t *out, uint32_t cap_records)
+{
+    if (ref_class_init() != 0) return -1;
+    g_null_tuner.Name = "none";
+    g_null_tuner.Init = tuner_ok;
+    g_null_tuner.InitProcess = tuner_ok;
+    g_null_tuner.SetBW = tuner_ok;
+    g_host.RequestState = CMD_SEND; /* what USBH_CtlReq leaves between requests (usbh_ctlreq.c) */
+    g_host.pUser = user_cb;
+    g_trace = (struct ref_ctl_rec *)out;
+    g_trace_cap = cap_records;
+    g_trace_n = 0;
+    g_i2c_last_addr = 0;
+    g_i2c_last_reg = 0;
+    long rc = -2;
+    for (int polls = 0; polls < 100000; ++polls) {
+        if (handle()->reqNumber == 28 && handle()->tuner == &Tuner_E4K) handle()->tuner = &g_null_tuner;
+        USBH_StatusTypeDef st = g_host.pActiveClass->Requests(&g_host);
+        if (st == USBH_OK) { rc = (long)g_trace_n; break; }
+        /* anything else means "call me again": USBH_Process only looks for USBH_OK (usbh_core.c:557-562), and the
+         * FSM's own return value is USBH_FAIL while a sub-FSM is busy (rStatus is never set in that branch) */
+    }
+    g_trace = 0;
+    return rc;
+}
+
 #ifdef REF_CLI
 static int cli_frontend(int argc, char **argv)
 {
+    if (strcmp(argv[1], "--init-trace") == 0 && argc >= 3) { /* writes the 12-byte records to argv[2] */
+        static uint8_t buf[12 * 4096];
+        long n = ref_init_trace(buf, 4096);
+        if (n < 0 || n > 4096) { fprintf(stderr, "init trace failed: %ld\n", n); return 1; }
+        FILE *f = fopen(argv[2], "wb");
+        if (!f) return 1;
+        fwrite(buf, 12, (size_t)n, f);
+        fclose(f);
+        printf("REF_INIT_TRACE %ld\n", n);
+        return 0;
+    }
     if (strcmp(argv[1], "--rate") == 0 && argc >= 3) {
         uint32_t a, b; double r;
         if (ref_set_sample_rate((uint32_t)strtoul(argv[2], 0, 0), &a, &b, &r)) return 1;

@@ -169,6 +169,26 @@ def rtl_fir_pack(coeff=None):
     return rc, bytes(out), list(c)
 
 
+class CtlXfer(C.Structure):
+    _fields_ = [("bmRequestType", C.c_uint8), ("bRequest", C.c_uint8), ("wValue", C.c_uint16), ("wIndex", C.c_uint16),
+                ("wLength", C.c_uint16), ("data", C.c_uint8 * 2), ("step", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+def rtl_init_sequence(samp_rate=240000, xtal_hz=28800000, fir=None, flags=1, capacity=256):
+    """include/b200sdr_frontend.h: (status, n, raw 12-byte records as bytes)."""
+    lib = load_library()
+    lib.b200sdr_rtl_init_sequence.restype = C.c_int32
+    lib.b200sdr_rtl_init_sequence.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, C.POINTER(CtlXfer),
+                                              C.c_uint32, C.POINTER(C.c_uint32)]
+    c = None
+    if fir is not None:
+        c = (C.c_int32 * 16)(*fir)
+    out = (CtlXfer * max(capacity, 1))()
+    n = C.c_uint32(0)
+    rc = lib.b200sdr_rtl_init_sequence(samp_rate, xtal_hz, c, flags, out if capacity else None, capacity, C.byref(n))
+    return rc, n.value, bytes(out)[: 12 * min(n.value, capacity)]
+
+
 def e4k_pll_params(fosc, intended_flo):
     lib = load_library()
     lib.b200sdr_e4k_pll_params.restype = C.c_uint32

@@ -52,6 +52,102 @@ int32_t b200sdr_rtl_fir_pack(const int32_t coeff[16], uint8_t out20[20])
     return in_range ? B200SDR_OK : B200SDR_NOT_SUPPORTED;
 }
 
+/* USBH_RTLSDR_ClassRequest, RTL/Src/usbh_rtlsdr.c:809-945, as a list of control transfers.  The emitters below
+ * restate the setup-packet encodings of RTLSDR_write_reg (:262-300), RTLSDR_demod_write_reg (:470-521, including
+ * the dummy read that follows every demod write, RTLSDR_demod_read_reg :445-468) and RTLSDR_i2c_read_reg
+ * (:347-398: one-byte write of the register number, one-byte read, both through block IICB). */
+namespace {
+struct SeqWriter {
+    b200sdr_ctl_xfer *out;
+    uint32_t capacity, n;
+    uint8_t step;
+    void emit(uint8_t type, uint16_t value, uint16_t index, uint16_t len, uint16_t val)
+    {
+        if (n < capacity) {
+            b200sdr_ctl_xfer x{};
+            x.bmRequestType = type;
+            x.wValue = value;
+            x.wIndex = index;
+            x.wLength = len;
+            if (type == 0x40) { /* 16-bit values travel high byte first */
+                x.data[0] = (uint8_t)(len == 1 ? val & 0xFF : val >> 8);
+                x.data[1] = (uint8_t)(len == 1 ? 0 : val & 0xFF);
+            }
+            x.step = step;
+            out[n] = x;
+        }
+        ++n;
+    }
+    void write_reg(uint8_t block, uint16_t addr, uint16_t val, uint8_t len) { emit(0x40, addr, (uint16_t)((block << 8) | 0x10), len, val); }
+    void demod_write(uint8_t page, uint16_t addr, uint16_t val, uint8_t len)
+    {
+        emit(0x40, (uint16_t)((addr << 8) | 0x20), (uint16_t)(0x10 | page), len, val);
+        emit(0xC0, (uint16_t)((0x01 << 8) | 0x20), 0x0a, 1, 0);
+    }
+    void i2c_read_reg(uint8_t chip, uint8_t reg)
+    {
+        emit(0x40, chip, (uint16_t)((6 << 8) | 0x10), 1, reg);
+        emit(0xC0, chip, (uint16_t)(6 << 8), 1, 0);
+    }
+};
+} // namespace
+
+int32_t b200sdr_rtl_init_sequence(uint32_t samp_rate, uint32_t xtal_hz, const int32_t *fir16, uint32_t flags,
+                                  b200sdr_ctl_xfer *out, uint32_t capacity, uint32_t *n_out)
+{
+    if (!n_out || (!out && capacity) || samp_rate == 0) return B200SDR_FAIL;
+    enum : uint8_t { USBB = 1, SYSB = 2 };                                  /* RTL/Inc/usbh_rtlsdr.h:319-327 */
+    enum : uint16_t { USB_SYSCTL = 0x2000, USB_EPA_CTL = 0x2148, USB_EPA_MAXPKT = 0x2158, DEMOD_CTL = 0x3000, DEMOD_CTL_1 = 0x300b };
+    int32_t coeff[16];
+    if (fir16) for (int i = 0; i < 16; ++i) coeff[i] = fir16[i];
+    else b200sdr_rtl_default_fir(coeff);
+    uint8_t fir[20];
+    const int32_t fir_rc = b200sdr_rtl_fir_pack(coeff, fir);
+    b200sdr_rtl_rate rate{};
+    const int32_t rate_rc = b200sdr_rtl_resampler(samp_rate, xtal_hz, &rate);
+
+    SeqWriter w{out, capacity, 0, 0};
+    w.step = 0;  w.write_reg(USBB, USB_SYSCTL, 0x09, 1);            /* dummy write */
+    w.step = 1;  w.write_reg(USBB, USB_SYSCTL, 0x09, 1);            /* initialise the USB block */
+    w.step = 2;  w.write_reg(USBB, USB_EPA_MAXPKT, 0x0002, 2);
+    w.step = 3;  w.write_reg(USBB, USB_EPA_CTL, 0x1002, 2);
+    w.step = 4;  w.write_reg(SYSB, DEMOD_CTL_1, 0x22, 1);           /* power the demodulator on */
+    w.step = 5;  w.write_reg(SYSB, DEMOD_CTL, 0xe8, 1);
+    w.step = 6;  w.demod_write(1, 0x01, 0x14, 1);                   /* soft reset on, off */
+    w.step = 7;  w.demod_write(1, 0x01, 0x10, 1);
+    w.step = 8;  w.demod_write(1, 0x15, 0x00, 1);                   /* no spectrum inversion / adjacent channel rejection */
+    w.step = 9;  w.demod_write(1, 0x16, 0x0000, 2);
+    for (uint8_t i = 0; i < 6; ++i) { w.step = (uint8_t)(10 + i); w.demod_write(1, (uint16_t)(0x16 + i), 0x00, 1); } /* DDC shift, IF */
+    w.step = 16; for (uint8_t i = 0; i < 20; ++i) w.demod_write(1, (uint16_t)(0x1c + i), fir[i], 1);
+    w.step = 17; w.demod_write(0, 0x19, 0x05, 1);                   /* SDR mode, DAGC off */
+    w.step = 18; w.demod_write(1, 0x93, 0xf0, 1);                   /* FSM state-holding register */
+    w.step = 19; w.demod_write(1, 0x94, 0x0f, 1);
+    w.step = 20; w.demod_write(1, 0x11, 0x00, 1);                   /* AGC off */
+    w.step = 21; w.demod_write(1, 0x04, 0x00, 1);                   /* RF and IF AGC loops off */
+    w.step = 22; w.demod_write(0, 0x61, 0x60, 1);                   /* PID filter off */
+    w.step = 23; w.demod_write(0, 0x06, 0x80, 1);                   /* default ADC_I / ADC_Q datapath */
+    w.step = 24; w.demod_write(1, 0xb1, 0x1b, 1);                   /* zero-IF, DC cancellation, IQ compensation */
+    w.step = 25; w.demod_write(0, 0x0d, 0x83, 1);                   /* no 4.096 MHz clock on TP_CK0 */
+    w.step = 26; w.demod_write(1, 0x01, 0x18, 1);                   /* I2C repeater on */
+    w.step = 27; w.i2c_read_reg(0xc8, 0x02);                        /* E4000 probe: E4K_I2C_ADDR, E4K_CHECK_ADDR */
+    /* 28, 29: tuner Init / InitProcess -- the tuner driver's own transfers */
+    w.step = 30;                                                    /* RTLSDR_set_sample_rate, states 1..9 (:700-790) */
+    w.demod_write(1, 0x01, 0x18, 1);                                /* repeater on; tuner SetBW; repeater on again */
+    w.demod_write(1, 0x01, 0x18, 1);
+    w.demod_write(1, 0x9f, (uint16_t)(rate.rsamp_ratio >> 16), 2);
+    w.demod_write(1, 0xa1, (uint16_t)(rate.rsamp_ratio & 0xffff), 2);
+    w.demod_write(1, 0x3f, 0, 1);                                   /* frequency correction 0 ppm, written twice */
+    w.demod_write(1, 0x3f, 0, 1);
+    w.demod_write(1, 0x01, 0x14, 1);                                /* soft reset on, off */
+    w.demod_write(1, 0x01, 0x10, 1);
+    w.step = 31; w.demod_write(0, 0x19, (flags & B200SDR_RTL_INIT_TEST_MODE) ? 0x03 : 0x05, 1);
+    w.step = 32; w.write_reg(USBB, USB_EPA_CTL, 0x1002, 2);         /* reset the bulk FIFO (mandatory) */
+    w.step = 33; w.write_reg(USBB, USB_EPA_CTL, 0x0000, 2);
+    *n_out = w.n;
+    if (w.n > capacity) return B200SDR_BUSY;
+    return (fir_rc != B200SDR_OK || rate_rc != B200SDR_OK) ? B200SDR_NOT_SUPPORTED : B200SDR_OK;
+}
+
 /* E4K_compute_pll_params, RTL/Src/tuner_e4k.c:689-737 with its band table :301-312 and
  * compute_fvco / compute_flo :338-361.  Fvco = Fosc (Z + X / 65536), Flo = Fvco / R.  The
  * reference stores Z in 8 and X in 16 bits before recomputing Flo; the same narrowing is applied. */

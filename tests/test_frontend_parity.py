@@ -141,3 +141,40 @@ def test_e4k_selection_bit_exact_against_reference(b):
     # the CLI agrees with the library (the path the other front-end tests use)
     assert ref("--e4k-rf", 2, 433920000) == ["3"]
     assert ref("--e4k-ifbw", 1, 2400000) == ["26", "2400000"]
+
+
+# ------------------------------------------------------------ register initialisation sequence as data
+def test_init_sequence_shape_and_errors(b):
+    rc, n, raw = b.rtl_init_sequence()
+    assert rc == 0 and n == 108 and len(raw) == 12 * 108
+    rec = np.frombuffer(raw, np.dtype([("t", "u1"), ("r", "u1"), ("v", "<u2"), ("i", "<u2"), ("l", "<u2"), ("d", "u1", 2),
+                                       ("step", "u1"), ("pad", "u1")]))
+    assert set(rec["t"]) == {0x40, 0xC0} and not rec["r"].any() and set(rec["l"]) <= {1, 2}
+    assert list(rec["step"]) == sorted(rec["step"]) and rec["step"][0] == 0 and rec["step"][-1] == 33
+    # the resampler ratio of 240 kS/s (0x0E000000) travels high byte first in two 16-bit writes
+    hi = rec[(rec["v"] == 0x9F20) & (rec["t"] == 0x40)][0]
+    lo = rec[(rec["v"] == 0xA120) & (rec["t"] == 0x40)][0]
+    assert bytes(hi["d"]) == b"\x0e\x00" and bytes(lo["d"]) == b"\x00\x00" and hi["l"] == 2
+    # 2.4 MS/s: ratio 0x03000000; test mode off selects the demodulator output (0x05)
+    rc, n, raw = b.rtl_init_sequence(2400000, flags=0)
+    rec2 = np.frombuffer(raw, rec.dtype)
+    assert rc == 0 and n == 108
+    assert bytes(rec2[(rec2["v"] == 0x9F20) & (rec2["t"] == 0x40)][0]["d"]) == b"\x03\x00"
+    assert rec2[(rec2["step"] == 31) & (rec2["t"] == 0x40)][0]["d"][0] == 0x05
+    # capacity too small: count still reported, BUSY; unsupported rate: NOT_SUPPORTED, list still produced
+    assert b.rtl_init_sequence(capacity=10)[:2] == (1, 108)
+    assert b.rtl_init_sequence(capacity=0)[:2] == (1, 108)
+    assert b.rtl_init_sequence(500000)[:2] == (3, 108)
+    assert b.rtl_init_sequence(0)[0] == 2
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+def test_init_sequence_bit_exact_against_reference(b, tmp_path):
+    """The reference's own, unmodified USBH_RTLSDR_ClassRequest polled to completion in oracle A with a recording
+    USBH_CtlReq: every setup packet and payload, in order, equals the product's list."""
+    path = str(tmp_path / "trace.bin")
+    assert ref("--init-trace", path) == ["108"]
+    want = open(path, "rb").read()
+    rc, n, got = b.rtl_init_sequence(240000, flags=1)
+    assert rc == 0 and n == 108
+    assert got == want
