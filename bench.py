@@ -347,6 +347,24 @@ def main():
     conv_gbs = 10.0 * Bc * CAPTURE_SAMPLES * args.steps / (ms_conv * 1e-3) / 1e9
     del cf
 
+    # K0 alone (test-mode counter check: 1 byte read per byte, nothing written), on counter captures -- what the
+    # firmware's stream really carries (RTLSDR_set_test_mode(phost, 1), usbh_rtlsdr.c:901).  The call includes its
+    # own result read-back (16 bytes per capture) and stream synchronisation.
+    Bk = min(B, 128)
+    cnt = torch.empty(Bk * CAPTURE_BYTES, dtype=torch.uint8, device="cuda")
+    for c in range(Bk):
+        sdr.synth_fill_dev(cnt.data_ptr() + c * CAPTURE_BYTES, 1, CAPTURE_BYTES, pkg.SYNTH_COUNTER, first_capture=c)
+    for _ in range(2):
+        n_breaks, _first = sdr.counter_check_dev(cnt.data_ptr(), Bk, CAPTURE_BYTES)
+    barrier()
+    sdr.timer_start()
+    for _ in range(args.steps):
+        n_breaks, _first = sdr.counter_check_dev(cnt.data_ptr(), Bk, CAPTURE_BYTES)
+    ms_cnt = max_over_ranks(sdr.timer_stop_ms())
+    cnt_gbs = 2.0 * Bk * CAPTURE_SAMPLES * args.steps / (ms_cnt * 1e-3) / 1e9
+    cnt_breaks = int(n_breaks.sum())
+    del cnt
+
     samples_step = B * CAPTURE_SAMPLES * world              # whole job, per step
     value = samples_step * args.steps / (ms_total * 1e-3) / 1e6
     hbm_peak, peak_src = load_peaks()
@@ -459,6 +477,11 @@ def main():
                 "convert_cf32": {"ms_per_step": ms_conv / args.steps, "MSps_per_gpu": Bc * CAPTURE_SAMPLES * args.steps / (ms_conv * 1e-3) / 1e6,
                                  "GBps": conv_gbs, "hbm_frac": conv_gbs / hbm_peak, "algorithmic_bytes_per_sample": 10.0,
                                  "note": "K2 alone over %d captures: HBM-bound reference, not part of `value`" % Bc},
+                "counter_check": {"ms_per_step": ms_cnt / args.steps, "MSps_per_gpu": Bk * CAPTURE_SAMPLES * args.steps / (ms_cnt * 1e-3) / 1e6,
+                                  "GBps": cnt_gbs, "hbm_frac": cnt_gbs / hbm_peak, "hbm_frac_nominal_8TBps": cnt_gbs / 8000.0,
+                                  "algorithmic_bytes_per_sample": 2.0, "breaks_found": cnt_breaks,
+                                  "note": "K0 alone over %d counter captures (the firmware's test-mode stream): HBM-bound, "
+                                          "not part of `value`" % Bk},
                 "am": {"ms_per_step": ms_am / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e6,
                        "GBps": am_gbs, "hbm_frac": am_gbs / hbm_peak, "hbm_frac_nominal_8TBps": am_gbs / 8000.0,
                        "algorithmic_bytes_per_sample": am_bytes,

@@ -213,6 +213,22 @@ B200SDR_API int32_t b200sdr_convert_cf32_dev(b200sdr_ctx *ctx, const uint8_t *iq
                                              float *out_dev);
 
 /* ------------------------------------------------------------------------------------------
+ * Test-mode counter check (kernel K0).  The firmware puts the RTL2832 into test mode before it starts
+ * streaming (RTLSDR_set_test_mode(phost, 1), RTL/Src/usbh_rtlsdr.c:901, :660-662), so the bytes that reach
+ * the buffer boundary are the dongle's 8-bit counter and every byte that is not its predecessor + 1 marks
+ * lost samples.  Per capture: n_breaks = number of indices i >= 1 with u[i] != (u[i-1] + 1) & 0xff, plus one
+ * for i = 0 when expect_first is 0..255 and u[0] differs from it (chain blocks with expect_first = last byte
+ * of the previous block + 1; -1 = do not check the first byte); first_break = the smallest such index or
+ * UINT64_MAX.  Results are written to HOST arrays of n_captures entries (either may be NULL); the call returns
+ * when they are valid.  `_dev`: captures resident in HBM, len_each a multiple of 4, 16-byte aligned pointer and
+ * stride (len_each a multiple of 16 unless n_captures == 1).  Host variant: one block of `len` bytes.
+ * ------------------------------------------------------------------------------------------ */
+B200SDR_API int32_t b200sdr_counter_check_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
+                                              int32_t expect_first, uint64_t *n_breaks_host, uint64_t *first_break_host);
+B200SDR_API int32_t b200sdr_counter_check(b200sdr_ctx *ctx, const uint8_t *iq_host, uint32_t len, int32_t expect_first,
+                                          uint64_t *n_breaks, uint64_t *first_break);
+
+/* ------------------------------------------------------------------------------------------
  * Presentation: a power spectrum as a 480 x 272 ARGB8888 bar plot --
  * the geometry and pixel format of the LCD layer the firmware's sample buffer aliases
  * (src/main.c:100-109).  Column 0 is -fs/2, the centre column is DC; dB = 10 log10(power) mapped

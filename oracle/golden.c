@@ -69,6 +69,25 @@ size_t gold_ingest_copy(uint8_t *dest, const uint8_t *fifo_bytes, uint16_t len)
     return (size_t)count32b * 4u;
 }
 
+/* ---- test-mode counter check: the firmware selects the RTL2832's test mode (RTLSDR_set_test_mode(phost, 1),
+ * RTL/Src/usbh_rtlsdr.c:901, :660-662), so the stream is an 8-bit counter; a byte that is not its predecessor
+ * + 1 (mod 256) is a break (lost samples).  expect_first in 0..255 also checks byte 0. */
+uint64_t gold_counter_check(const uint8_t *u, size_t len, int expect_first, uint64_t *first_break)
+{
+    uint64_t n = 0, first = UINT64_MAX;
+    for (size_t i = 0; i < len; ++i) {
+        int bad;
+        if (i == 0) bad = expect_first >= 0 && u[0] != (uint8_t)expect_first;
+        else bad = u[i] != (uint8_t)(u[i - 1] + 1);
+        if (bad) {
+            n++;
+            if (first == UINT64_MAX) first = i;
+        }
+    }
+    if (first_break) *first_break = first;
+    return n;
+}
+
 /* ---- conversion ------------------------------------------------------------------------- */
 void gold_convert(const uint8_t *iq, size_t n, real *out)
 {

@@ -48,6 +48,8 @@ int gold_sizeof_real(void);
 
 /* restatement of USB_ReadPacket (stm32f7xx_ll_usb.c:792-803); returns bytes written (whole words) */
 size_t gold_ingest_copy(uint8_t *dest, const uint8_t *fifo_bytes, uint16_t len);
+/* test-mode counter stream: number of breaks, *first_break = smallest index or UINT64_MAX */
+uint64_t gold_counter_check(const uint8_t *u, size_t len, int expect_first, uint64_t *first_break);
 const float *gold_synth_lut(void);
 
 /* x[n] = (I - 127.5) + j (Q - 127.5); out is interleaved re,im; n complex samples */

@@ -85,6 +85,8 @@ def load_library():
         "b200sdr_am_audio_len": (u64, [u64]),
         "b200sdr_convert_cf32": (i32, [vp, u8p, u32, u32, f32p]),
         "b200sdr_convert_cf32_dev": (i32, [vp, u8p, u64, u32, f32p]),
+        "b200sdr_counter_check_dev": (i32, [vp, u8p, u32, u64, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
+        "b200sdr_counter_check": (i32, [vp, u8p, u32, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
         "b200sdr_get_taps": (i32, [vp, u32, f32p, u32, C.POINTER(u32)]),
         "b200sdr_get_window": (i32, [vp, u32, f32p]),
         "b200sdr_debug_last_block": (i32, [vp, u8p, u32, C.POINTER(u32)]),
@@ -391,6 +393,23 @@ class B200Sdr:
         finally:
             self.dev_free(d_iq), self.dev_free(d_a), self.dev_free(d_d)
         return audio, disc
+
+    def counter_check(self, iq, expect_first=-1):
+        """b200sdr_counter_check (one host block): (n_breaks, first_break or None)."""
+        iq = _u8(iq)
+        n, f = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.b200sdr_counter_check(self.ctx, iq.ctypes.data if iq.size else None, iq.size, expect_first,
+                                                   C.byref(n), C.byref(f)), "b200sdr_counter_check")
+        return n.value, (None if f.value == 2**64 - 1 else f.value)
+
+    def counter_check_dev(self, iq_dev, n_captures, len_each, expect_first=-1):
+        """b200sdr_counter_check_dev: (n_breaks[n_captures], first_break[n_captures]) as uint64 arrays."""
+        n = np.zeros(n_captures, np.uint64)
+        f = np.zeros(n_captures, np.uint64)
+        self._check(self.lib.b200sdr_counter_check_dev(self.ctx, iq_dev, n_captures, len_each, expect_first,
+                                                       n.ctypes.data_as(C.POINTER(C.c_uint64)), f.ctypes.data_as(C.POINTER(C.c_uint64))),
+                    "b200sdr_counter_check_dev")
+        return n, f
 
     def am(self, iq, n_captures=1):
         iq = _u8(iq)

@@ -50,6 +50,8 @@ struct b200sdr_ctx {
 
     /* constants on the device */
     float *d_window[3] = {nullptr, nullptr, nullptr};
+    unsigned long long *d_counter_res = nullptr; /* K0 results: [n] break counts, [n] first breaks */
+    uint32_t counter_res_cap = 0;
     float2 *d_twiddle = nullptr;
     float *d_lut = nullptr;
     float *d_thresholds = nullptr;
@@ -614,7 +616,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
-                        ctx->d_res_am};
+                        ctx->d_res_am, ctx->d_counter_res};
     for (void *p : dev_ptrs) if (p) cudaFree(p);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -921,6 +923,75 @@ int32_t b200sdr_convert_cf32(b200sdr_ctx *ctx, const uint8_t *iq_host, uint32_t 
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "convert", e);
     return B200SDR_OK;
+}
+
+/* ---- test-mode counter check (kernel K0) ---------------------------------------------------- */
+int32_t b200sdr_counter_check_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
+                                  int32_t expect_first, uint64_t *n_breaks_host, uint64_t *first_break_host)
+{
+    if (!ctx) return B200SDR_FAIL;
+    if (n_captures == 0) return B200SDR_OK;
+    if (!iq_dev) return fail(ctx, B200SDR_FAIL, "null capture pointer");
+    if ((len_each & 3u) || !aligned16(iq_dev) || (n_captures > 1 && (len_each & 15u)) || n_captures > 65535u || expect_first > 255)
+        return fail(ctx, B200SDR_NOT_SUPPORTED, "counter check needs len % 4 == 0, a 16-byte aligned pointer and stride, <= 65535 captures");
+    DeviceGuard guard(ctx->device);
+    if (ctx->counter_res_cap < n_captures) { /* grown on demand, kept: no allocation on the repeated call */
+        if (ctx->d_counter_res) { CU(cudaStreamSynchronize(ctx->s_compute)); CU(cudaFree(ctx->d_counter_res)); }
+        ctx->d_counter_res = nullptr;
+        ctx->counter_res_cap = 0;
+        CU(cudaMalloc((void **)&ctx->d_counter_res, 2u * (size_t)n_captures * sizeof(unsigned long long)));
+        ctx->counter_res_cap = n_captures;
+    }
+    unsigned long long *d_res = ctx->d_counter_res;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaMemsetAsync(d_res, 0, n_captures * sizeof(unsigned long long), ctx->s_compute)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(d_res + n_captures, 0xff, n_captures * sizeof(unsigned long long), ctx->s_compute)) != cudaSuccess) break;
+        if (len_each) {
+            CounterParams p{};
+            p.in = reinterpret_cast<const uint32_t *>(iq_dev);
+            p.stride_words = len_each / 4u;
+            p.n_words = len_each / 4u;
+            p.expect_first = expect_first < 0 ? -1 : expect_first;
+            p.n_breaks = d_res;
+            p.first_break = d_res + n_captures;
+            const uint64_t n_vec = len_each / 16u;
+            const uint64_t blocks = n_vec ? b200::ceil_div(n_vec, 1024) : 1;
+            if (blocks > 0x7fffffffull) return fail(ctx, B200SDR_NOT_SUPPORTED, "capture too long");
+            k_counter_check<<<dim3((unsigned)blocks, n_captures), 256, 0, ctx->s_compute>>>(p);
+            if ((e = cudaGetLastError()) != cudaSuccess) break;
+            ctx->launches += 1;
+        }
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "result layout");
+        if (n_breaks_host &&
+            (e = cudaMemcpyAsync(n_breaks_host, d_res, n_captures * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->s_compute)) != cudaSuccess) break;
+        if (first_break_host &&
+            (e = cudaMemcpyAsync(first_break_host, d_res + n_captures, n_captures * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->s_compute)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(ctx->s_compute);
+    } while (0);
+    if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "counter check", e);
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_counter_check(b200sdr_ctx *ctx, const uint8_t *iq_host, uint32_t len, int32_t expect_first, uint64_t *n_breaks,
+                              uint64_t *first_break)
+{
+    if (!ctx || (!iq_host && len)) return B200SDR_FAIL;
+    if (len & 3u) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4");
+    if (len == 0) {
+        if (n_breaks) *n_breaks = 0;
+        if (first_break) *first_break = ~0ull;
+        return B200SDR_OK;
+    }
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in = nullptr;
+    CU(cudaMalloc((void **)&d_in, len));
+    cudaError_t e = cudaMemcpyAsync(d_in, iq_host, len, cudaMemcpyHostToDevice, ctx->s_compute);
+    int rc = B200SDR_OK;
+    if (e == cudaSuccess) rc = b200sdr_counter_check_dev(ctx, d_in, 1, len, expect_first, n_breaks, first_break);
+    cudaFree(d_in);
+    if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "counter check copy", e);
+    return rc;
 }
 
 int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *out, uint32_t capacity, uint32_t *n_taps)

@@ -43,6 +43,102 @@ __global__ void __launch_bounds__(256) k_convert_cf32(const uint32_t *__restrict
     }
 }
 
+/* K0: test-mode counter check.  The firmware switches the RTL2832 into test mode before it starts the bulk
+ * transfers (RTLSDR_set_test_mode(phost, 1), RTL/Src/usbh_rtlsdr.c:901 and :660-662), so the byte stream that
+ * reaches the buffer boundary is the dongle's 8-bit counter: u[i] = u[i-1] + 1 (mod 256).  A byte that is not
+ * its predecessor + 1 marks lost samples (what rtl_test counts).  This kernel counts those breaks and finds the
+ * first one, per capture; the only HBM-bound chain of the path next to K2: 1 byte read per byte, nothing written.
+ *   a break at index i (1 <= i < len)  <=>  u[i] != (u[i-1] + 1) & 0xff;  i = 0 breaks iff expect_first >= 0 and
+ *   u[0] != expect_first (the value that continues the previous block).
+ * A thread takes four 16-byte vectors 256 vectors apart (every warp load is 512 contiguous bytes); inside a
+ * word the four byte lanes are compared at once: s = the word shifted down one byte with the next word's first
+ * byte on top (funnel shift) must equal the word with every byte incremented.  The next vector's first word comes
+ * from the neighbouring lane (lane 31 reads it).  `n_vec` = capture length / 16, `n_words` = length / 4 (the tail of a
+ * length that is not a multiple of 16 is handled word by word by the last block). */
+struct CounterParams {
+    const uint32_t *in;      /* capture c at in + c * stride_words */
+    uint64_t stride_words, n_words;
+    int32_t expect_first;    /* -1: the first byte is not checked */
+    unsigned long long *n_breaks, *first_break; /* [capture]; preset to 0 and ~0 */
+};
+
+/* bytes of the result are non-zero where the successor of a byte of `w` is not that byte + 1.  The per-byte
+ * increment is done inside the 32-bit word without carries between the lanes (low seven bits added, top bit
+ * xor-ed back): five integer instructions per word -- the byte-SIMD intrinsics (__vsub4, __vcmpne4) are emulated
+ * with three times as many on this architecture and made the kernel issue-bound at 55 % of the HBM roofline. */
+__device__ __forceinline__ uint32_t b200_counter_diff(uint32_t w, uint32_t next)
+{
+    const uint32_t s = __funnelshift_r(w, next, 8);                                   /* bytes (b1, b2, b3, next.b0) */
+    const uint32_t w1 = ((w & 0x7f7f7f7fu) + 0x01010101u) ^ (w & 0x80808080u);         /* (b0+1, b1+1, b2+1, b3+1) mod 256 */
+    return s ^ w1;
+}
+/* the rare path: count the non-zero bytes of `ne` (word `word_idx` of the capture) and note the first */
+__device__ __forceinline__ void b200_counter_note(uint32_t ne, uint64_t word_idx, uint32_t &count, uint64_t &first)
+{
+    if (ne == 0u) return;
+    const uint32_t flags = (((ne & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ne) & 0x80808080u;   /* 0x80 per non-zero byte */
+    count += (uint32_t)__popc(flags);
+    const uint64_t pos = word_idx * 4u + (uint32_t)((__ffs((int)flags) - 1) >> 3) + 1u; /* index of the offending byte */
+    if (pos < first) first = pos;
+}
+
+__global__ void __launch_bounds__(256) k_counter_check(CounterParams p)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t *in = p.in + (uint64_t)c * p.stride_words;
+    const uint64_t n_vec = p.n_words / 4u;
+    const int lane = (int)(threadIdx.x & 31u);
+    uint32_t count = 0;
+    uint64_t first = ~0ull;
+    const uint64_t base = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
+    uint4 vv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { /* all four loads in flight before the first use */
+        const uint64_t j = base + 256u * k;
+        vv[k] = j < n_vec ? __ldcs(reinterpret_cast<const uint4 *>(in) + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t j = base + 256u * k;
+        const uint4 v = vv[k];
+        /* first word of the next vector: the neighbouring lane has it; lane 31 and the last vector read it;
+         * the very last byte of a capture has no successor, so it is given the one it expects */
+        uint32_t next = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (lane == 31 || j + 1 >= n_vec) next = (j + 1) * 4u < p.n_words ? __ldg(in + (j + 1) * 4u) : (v.w >> 24) + 1u;
+        if (j < n_vec) {
+            const uint32_t e0 = b200_counter_diff(v.x, v.y), e1 = b200_counter_diff(v.y, v.z);
+            const uint32_t e2 = b200_counter_diff(v.z, v.w), e3 = b200_counter_diff(v.w, next);
+            if (e0 | e1 | e2 | e3) {
+                b200_counter_note(e0, 4u * j, count, first);
+                b200_counter_note(e1, 4u * j + 1u, count, first);
+                b200_counter_note(e2, 4u * j + 2u, count, first);
+                b200_counter_note(e3, 4u * j + 3u, count, first);
+            }
+        }
+    }
+    /* words past the last whole vector (length % 16 != 0) and the first byte: one thread */
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (uint64_t w = n_vec * 4u; w < p.n_words; ++w)
+            b200_counter_note(b200_counter_diff(in[w], w + 1 < p.n_words ? in[w + 1] : (in[w] >> 24) + 1u), w, count, first);
+        if (p.expect_first >= 0 && p.n_words > 0 && (in[0] & 0xffu) != (uint32_t)p.expect_first) {
+            count += 1;
+            first = 0;
+        }
+    }
+    if (__any_sync(0xffffffffu, first != ~0ull)) { /* rare: a clean stream never gets here */
+        count = __reduce_add_sync(0xffffffffu, count);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, first, o);
+            if (other < first) first = other;
+        }
+        if (lane == 0) {
+            atomicAdd(p.n_breaks + c, (unsigned long long)count);
+            atomicMin(p.first_break + c, (unsigned long long)first);
+        }
+    }
+}
+
 /* synthetic captures: one thread per 8 complex samples (16 bytes) */
 __global__ void __launch_bounds__(256) k_synth(uint4 *__restrict__ out, uint64_t groups_per_capture,
                                                uint64_t capture_stride16, uint32_t kind, uint64_t first_capture,

@@ -20,6 +20,8 @@ def _load(name):
     lib.gold_ingest_copy.restype = sz
     lib.gold_ingest_copy.argtypes = [vp, vp, C.c_uint16]
     lib.gold_convert.argtypes = [vp, sz, vp]
+    lib.gold_counter_check.restype = u64
+    lib.gold_counter_check.argtypes = [vp, sz, C.c_int, C.POINTER(u64)]
     lib.gold_convert_window.argtypes = [vp, sz, C.c_int, vp]
     lib.gold_window.argtypes = [C.c_int, C.c_int, vp]
     lib.gold_fft.argtypes = [vp, vp, C.c_int]
@@ -54,6 +56,12 @@ class Golden:
         buf = np.zeros(n_captures * len_each + 64, np.uint8)  # padded: kernels may read to a 16-byte boundary
         self.lib.gold_synth_fill(buf.ctypes.data, n_captures, len_each, kind, first_capture)
         return buf[: n_captures * len_each]
+
+    def counter_check(self, iq, expect_first=-1):
+        iq = np.ascontiguousarray(iq, np.uint8)
+        first = C.c_uint64(0)
+        n = self.lib.gold_counter_check(iq.ctypes.data, iq.size, expect_first, C.byref(first))
+        return int(n), (None if first.value == 2**64 - 1 else int(first.value))
 
     def convert(self, iq, window=None):
         iq = np.ascontiguousarray(iq, np.uint8)

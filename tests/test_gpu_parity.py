@@ -219,6 +219,59 @@ def test_wbfm_host_path_equals_device_path(sdr, g):
     assert np.array_equal(a_host, a_dev)
 
 
+# ------------------------------------------------------------------------- test-mode counter (K0)
+@pytest.mark.parametrize("nbytes", [0, 4, 12, 16, 20, 1020, 16384 + 8, 262144, 4 * 262144 + 4])
+def test_counter_check_host_blocks(sdr, g, nbytes):
+    """bit-exact against gold_counter_check: clean counter, injected breaks (also on word, vector, warp and block
+    boundaries and on the last byte), first-byte expectation."""
+    rng = np.random.default_rng(nbytes)
+    clean = (np.arange(nbytes) + 201).astype(np.uint8)
+    assert sdr.counter_check(clean) == (0, None) == g.counter_check(clean)
+    assert sdr.counter_check(clean, 201 if nbytes else -1) == (0, None)
+    if nbytes == 0:
+        return
+    assert sdr.counter_check(clean, 7) == (1, 0) == g.counter_check(clean, 7)
+    for _ in range(4):
+        u = clean.copy()
+        where = list(rng.integers(0, nbytes, size=5)) + [nbytes - 1, 3, 4, 15, 16, 511, 512, 16383, 16384]
+        where = [w for w in where if w < nbytes]
+        u[where] = rng.integers(0, 256, size=len(where), dtype=np.uint8)
+        for expect in (-1, int(clean[0])):
+            assert sdr.counter_check(u, expect) == g.counter_check(u, expect)
+
+
+def test_counter_check_batch_dev(sdr, g):
+    """the device generator's counter captures are clean; every capture is judged on its own (no carry from the
+    previous capture's last byte); a dropped sector shows up as one break at the right place."""
+    n_captures, len_each = 5, 3 * 262144 + 16
+    d = sdr.dev_alloc(n_captures * len_each)
+    try:
+        sdr.synth_fill_dev(d, n_captures, len_each, SYNTH_COUNTER, 0)
+        n, f = sdr.counter_check_dev(d, n_captures, len_each)
+        assert not n.any() and (f == np.uint64(2**64 - 1)).all()
+        host = sdr.to_host(d, n_captures * len_each, np.uint8).reshape(n_captures, len_each).copy()
+        host[2, 1000:] = np.roll(host[2], -32)[1000:]  # 32 bytes lost at index 1000 (and the rolled-in head near the end)
+        host[4, 70000] ^= 0x40
+        sdr.to_dev(d, host.reshape(-1))
+        n, f = sdr.counter_check_dev(d, n_captures, len_each)
+        for c in range(n_captures):
+            want_n, want_f = g.counter_check(host[c])
+            assert (int(n[c]), None if f[c] == np.uint64(2**64 - 1) else int(f[c])) == (want_n, want_f), c
+        assert int(n[2]) >= 1 and int(f[2]) == 1000 and int(n[4]) == 2 and int(f[4]) == 70000
+    finally:
+        sdr.dev_free(d)
+
+
+def test_counter_check_rejects_bad_arguments(sdr, sdr_lib):
+    d = sdr.dev_alloc(64)
+    try:
+        for args in ((d, 1, 6), (d + 4, 1, 16), (d, 2, 20)):
+            with pytest.raises(sdr_lib.B200SdrError):
+                sdr.counter_check_dev(*args)
+    finally:
+        sdr.dev_free(d)
+
+
 # ------------------------------------------------------------------------------------------ AM
 def test_am_golden_fixture(sdr, sdr_lib, vec):
     iq = sdr_lib.synth_fill_host(1, int(vec["am_len"]), SYNTH_AM, int(vec["am_seed"]))

@@ -196,3 +196,19 @@ def test_counter_stream_is_the_rtl2832_test_pattern(g):
     # test mode (reference usbh_rtlsdr.c:901): an 8-bit counter; b[i+1] == b[i] + 1 mod 256
     b = g.synth(1, 4096, SYNTH_COUNTER, 0).astype(np.int32)
     assert np.all((b[1:] - b[:-1]) % 256 == 1) and b[0] == 0
+
+
+def test_counter_check_against_numpy(g):
+    """gold_counter_check (the checker of kernel K0) against a two-line numpy statement of the same definition."""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 4, 255, 256, 257, 4096, 100003):
+        u = (np.arange(n) + 37).astype(np.uint8)
+        hits = rng.integers(0, max(n, 1), size=min(n, 7))
+        u[hits] = rng.integers(0, 256, size=hits.size, dtype=np.uint8) if n else u[hits]
+        for expect in (-1, 37, 38):
+            bad = np.zeros(n, bool)
+            if n:
+                bad[1:] = u[1:] != (u[:-1].astype(np.int64) + 1) % 256
+                bad[0] = expect >= 0 and u[0] != expect
+            idx = np.flatnonzero(bad)
+            assert g.counter_check(u, expect) == (idx.size, int(idx[0]) if idx.size else None)
