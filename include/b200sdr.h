@@ -46,6 +46,7 @@ extern "C" {
 #define B200SDR_CHAIN_SPECTRUM 1u /* u8 -> window -> 1024-pt FFT -> |X|^2 -> average      */
 #define B200SDR_CHAIN_WBFM     2u /* u8 -> /10 polyphase FIR -> discriminator -> de-emph -> /5 -> 48 kHz */
 #define B200SDR_CHAIN_AM       4u /* u8 -> /20 -> /10 -> envelope -> DC block -> x2//3 -> 8 kHz */
+#define B200SDR_CHAIN_COUNTER  8u /* test-mode counter check (lost samples), see b200sdr_counter_check; streaming only */
 
 #define B200SDR_WINDOW_RECT     0u
 #define B200SDR_WINDOW_HANN     1u /* periodic: w[n] = 0.5 - 0.5 cos(2 pi n / N)           */
@@ -227,6 +228,11 @@ B200SDR_API int32_t b200sdr_counter_check_dev(b200sdr_ctx *ctx, const uint8_t *i
                                               int32_t expect_first, uint64_t *n_breaks_host, uint64_t *first_break_host);
 B200SDR_API int32_t b200sdr_counter_check(b200sdr_ctx *ctx, const uint8_t *iq_host, uint32_t len, int32_t expect_first,
                                           uint64_t *n_breaks, uint64_t *first_break);
+/* Streaming: with B200SDR_CHAIN_COUNTER in cfg.chains every block accepted by process_samples() is checked as a
+ * continuation of the previous one (the last byte is carried on the device).  Totals since create / reset:
+ * *n_breaks, and *first_break = index of the first offending byte counted from the start of the stream
+ * (UINT64_MAX: none).  Covers every accepted block (pending bytes are submitted first, like b200sdr_get_spectrum). */
+B200SDR_API int32_t b200sdr_get_counter_check(b200sdr_ctx *ctx, uint64_t *n_breaks, uint64_t *first_break);
 
 /* ------------------------------------------------------------------------------------------
  * Presentation: a power spectrum as a 480 x 272 ARGB8888 bar plot --

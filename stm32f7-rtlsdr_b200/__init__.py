@@ -17,6 +17,7 @@ from .binding import (  # noqa: F401
     CHAIN_SPECTRUM,
     CHAIN_WBFM,
     CHAIN_AM,
+    CHAIN_COUNTER,
     WINDOW_RECT,
     WINDOW_HANN,
     WINDOW_BLACKMAN,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libb200sdr.so")
 HEADER_PATH = os.path.join(HERE, "..", "include", "b200sdr.h")
 
 OK, BUSY, FAIL, NOT_SUPPORTED, UNRECOVERED_ERROR = 0, 1, 2, 3, 4
-CHAIN_SPECTRUM, CHAIN_WBFM, CHAIN_AM = 1, 2, 4
+CHAIN_SPECTRUM, CHAIN_WBFM, CHAIN_AM, CHAIN_COUNTER = 1, 2, 4, 8
 WINDOW_RECT, WINDOW_HANN, WINDOW_BLACKMAN = 0, 1, 2
 AVG_MEAN, AVG_EMA = 0, 1
 SYNTH_COUNTER, SYNTH_MULTITONE, SYNTH_WBFM, SYNTH_AM = 0, 1, 2, 3
@@ -87,6 +87,7 @@ def load_library():
         "b200sdr_convert_cf32_dev": (i32, [vp, u8p, u64, u32, f32p]),
         "b200sdr_counter_check_dev": (i32, [vp, u8p, u32, u64, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
         "b200sdr_counter_check": (i32, [vp, u8p, u32, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
+        "b200sdr_get_counter_check": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "b200sdr_get_taps": (i32, [vp, u32, f32p, u32, C.POINTER(u32)]),
         "b200sdr_get_window": (i32, [vp, u32, f32p]),
         "b200sdr_debug_last_block": (i32, [vp, u8p, u32, C.POINTER(u32)]),
@@ -400,6 +401,12 @@ class B200Sdr:
         n, f = C.c_uint64(0), C.c_uint64(0)
         self._check(self.lib.b200sdr_counter_check(self.ctx, iq.ctypes.data if iq.size else None, iq.size, expect_first,
                                                    C.byref(n), C.byref(f)), "b200sdr_counter_check")
+        return n.value, (None if f.value == 2**64 - 1 else f.value)
+
+    def get_counter_check(self):
+        """streaming totals (CHAIN_COUNTER): (n_breaks, first_break or None)."""
+        n, f = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.b200sdr_get_counter_check(self.ctx, C.byref(n), C.byref(f)), "b200sdr_get_counter_check")
         return n.value, (None if f.value == 2**64 - 1 else f.value)
 
     def counter_check_dev(self, iq_dev, n_captures, len_each, expect_first=-1):

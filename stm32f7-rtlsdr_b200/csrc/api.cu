@@ -52,6 +52,8 @@ struct b200sdr_ctx {
     float *d_window[3] = {nullptr, nullptr, nullptr};
     unsigned long long *d_counter_res = nullptr; /* K0 results: [n] break counts, [n] first breaks */
     uint32_t counter_res_cap = 0;
+    CounterStreamState *d_cnt_state = nullptr; /* streaming K0: totals + the byte the next block must start with */
+    uint64_t cnt_bytes = 0;                    /* stream bytes already checked (absolute index of the next block) */
     float2 *d_twiddle = nullptr;
     float *d_lut = nullptr;
     float *d_thresholds = nullptr;
@@ -319,6 +321,31 @@ int stream_am(b200sdr_ctx *ctx)
     return B200SDR_OK;
 }
 
+int stream_counter(b200sdr_ctx *ctx, uint32_t len)
+{
+    if (len == 0) return B200SDR_OK;
+    CounterParams p{};
+    p.in = reinterpret_cast<const uint32_t *>(ctx->d_stream + ctx->last_pos); /* blocks are multiples of 4 bytes */
+    p.n_words = len / 4u;
+    p.stride_words = p.n_words;
+    p.expect_first = -1;
+    p.stream = ctx->d_cnt_state;
+    p.pos_base = ctx->cnt_bytes;
+    k_counter_check<<<dim3((unsigned)b200::ceil_div(b200::ceil_div(p.n_words, 4), 1024), 1), 256, 0, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->cnt_bytes += len;
+    return B200SDR_OK;
+}
+
+int reset_counter_state(b200sdr_ctx *ctx)
+{
+    static const CounterStreamState init = {0ull, ~0ull, 0xffffffffu, 0u};
+    ctx->cnt_bytes = 0;
+    CU(cudaMemcpyAsync(ctx->d_cnt_state, &init, sizeof init, cudaMemcpyHostToDevice, ctx->s_compute));
+    return B200SDR_OK;
+}
+
 int reset_stream_state(b200sdr_ctx *ctx)
 {
     ctx->wpos = ctx->spec_off = ctx->fm_off = ctx->am_off = ctx->last_pos = 0;
@@ -331,7 +358,7 @@ int reset_stream_state(b200sdr_ctx *ctx)
     CU(cudaMemsetAsync(ctx->d_amf_state, 0, 2 * sizeof(AmFrontState), ctx->s_compute));
     ctx->amf_state_cur = 0;
     CU(cudaMemsetAsync(ctx->d_amb_state, 0, sizeof(AmBackState), ctx->s_compute));
-    return B200SDR_OK;
+    return reset_counter_state(ctx);
 }
 
 const float *synth_lut_host()
@@ -385,6 +412,7 @@ int commit_slot(b200sdr_ctx *ctx, uint32_t slot, uint32_t len)
     if (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM) { rc = stream_spectrum(ctx); if (rc) return rc; }
     if (ctx->cfg.chains & B200SDR_CHAIN_WBFM) { rc = stream_wbfm(ctx); if (rc) return rc; }
     if (ctx->cfg.chains & B200SDR_CHAIN_AM) { rc = stream_am(ctx); if (rc) return rc; }
+    if (ctx->cfg.chains & B200SDR_CHAIN_COUNTER) { rc = stream_counter(ctx, len); if (rc) return rc; }
     ctx->slot_used[slot] = 1;
     ctx->submits += 1;
     ctx->ring_head = (slot + 1) % ctx->cfg.ring_slots;
@@ -574,6 +602,7 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
         CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
     CK(cudaMalloc((void **)&ctx->d_spec_acc, 1024 * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->d_cnt_state, sizeof(CounterStreamState)));
     CK(cudaMalloc((void **)&ctx->d_fm_state, 2 * sizeof(FmState)));
     CK(cudaMalloc((void **)&ctx->d_amf_state, 2 * sizeof(AmFrontState)));
     CK(cudaMalloc((void **)&ctx->d_amb_state, sizeof(AmBackState)));
@@ -616,7 +645,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
-                        ctx->d_res_am, ctx->d_counter_res};
+                        ctx->d_res_am, ctx->d_counter_res, ctx->d_cnt_state};
     for (void *p : dev_ptrs) if (p) cudaFree(p);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -970,6 +999,21 @@ int32_t b200sdr_counter_check_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint3
         e = cudaStreamSynchronize(ctx->s_compute);
     } while (0);
     if (e != cudaSuccess) return fail(ctx, B200SDR_FAIL, "counter check", e);
+    return B200SDR_OK;
+}
+
+int32_t b200sdr_get_counter_check(b200sdr_ctx *ctx, uint64_t *n_breaks, uint64_t *first_break)
+{
+    if (!ctx) return B200SDR_FAIL;
+    if (!(ctx->cfg.chains & B200SDR_CHAIN_COUNTER)) return fail(ctx, B200SDR_NOT_SUPPORTED, "B200SDR_CHAIN_COUNTER is not enabled");
+    DeviceGuard guard(ctx->device);
+    int rc = flush_pending(ctx);
+    if (rc) return rc;
+    CounterStreamState st{};
+    CU(cudaMemcpyAsync(&st, ctx->d_cnt_state, sizeof st, cudaMemcpyDeviceToHost, ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    if (n_breaks) *n_breaks = st.n_breaks;
+    if (first_break) *first_break = st.first_break;
     return B200SDR_OK;
 }
 

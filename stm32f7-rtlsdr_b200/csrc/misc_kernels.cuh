@@ -55,11 +55,19 @@ __global__ void __launch_bounds__(256) k_convert_cf32(const uint32_t *__restrict
  * byte on top (funnel shift) must equal the word with every byte incremented.  The next vector's first word comes
  * from the neighbouring lane (lane 31 reads it).  `n_vec` = capture length / 16, `n_words` = length / 4 (the tail of a
  * length that is not a multiple of 16 is handled word by word by the last block). */
+struct CounterStreamState {      /* carried from block to block by the streaming path (one capture) */
+    unsigned long long n_breaks, first_break; /* first_break: absolute byte index in the stream, ~0 = none */
+    uint32_t expect;             /* value the next block's first byte must have; > 255: nothing known yet */
+    uint32_t pad;
+};
 struct CounterParams {
-    const uint32_t *in;      /* capture c at in + c * stride_words */
+    const uint32_t *in;      /* capture c at in + c * stride_words; 4-byte aligned (batches: 16-byte aligned) */
     uint64_t stride_words, n_words;
-    int32_t expect_first;    /* -1: the first byte is not checked */
+    int32_t expect_first;    /* -1: the first byte is not checked (ignored when `stream` is set) */
     unsigned long long *n_breaks, *first_break; /* [capture]; preset to 0 and ~0 */
+    CounterStreamState *stream; /* optional, one capture: results are accumulated here with `pos_base` added,
+                                   the first byte is checked against stream->expect, and expect is updated */
+    uint64_t pos_base;       /* absolute byte index of in[0] in the stream */
 };
 
 /* bytes of the result are non-zero where the successor of a byte of `w` is not that byte + 1.  The per-byte
@@ -85,8 +93,12 @@ __device__ __forceinline__ void b200_counter_note(uint32_t ne, uint64_t word_idx
 __global__ void __launch_bounds__(256) k_counter_check(CounterParams p)
 {
     const uint32_t c = blockIdx.y;
-    const uint32_t *in = p.in + (uint64_t)c * p.stride_words;
-    const uint64_t n_vec = p.n_words / 4u;
+    const uint32_t *in0 = p.in + (uint64_t)c * p.stride_words;
+    /* words before the first 16-byte boundary (streaming blocks start on any word), whole vectors, tail words */
+    uint64_t head = ((16u - (uint32_t)((uintptr_t)in0 & 15u)) & 15u) >> 2;
+    if (head > p.n_words) head = p.n_words;
+    const uint32_t *in = in0 + head;
+    const uint64_t rest = p.n_words - head, n_vec = rest / 4u;
     const int lane = (int)(threadIdx.x & 31u);
     uint32_t count = 0;
     uint64_t first = ~0ull;
@@ -104,26 +116,32 @@ __global__ void __launch_bounds__(256) k_counter_check(CounterParams p)
         /* first word of the next vector: the neighbouring lane has it; lane 31 and the last vector read it;
          * the very last byte of a capture has no successor, so it is given the one it expects */
         uint32_t next = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 31 || j + 1 >= n_vec) next = (j + 1) * 4u < p.n_words ? __ldg(in + (j + 1) * 4u) : (v.w >> 24) + 1u;
+        if (lane == 31 || j + 1 >= n_vec) next = (j + 1) * 4u < rest ? __ldg(in + (j + 1) * 4u) : (v.w >> 24) + 1u;
         if (j < n_vec) {
             const uint32_t e0 = b200_counter_diff(v.x, v.y), e1 = b200_counter_diff(v.y, v.z);
             const uint32_t e2 = b200_counter_diff(v.z, v.w), e3 = b200_counter_diff(v.w, next);
             if (e0 | e1 | e2 | e3) {
-                b200_counter_note(e0, 4u * j, count, first);
-                b200_counter_note(e1, 4u * j + 1u, count, first);
-                b200_counter_note(e2, 4u * j + 2u, count, first);
-                b200_counter_note(e3, 4u * j + 3u, count, first);
+                b200_counter_note(e0, head + 4u * j, count, first);
+                b200_counter_note(e1, head + 4u * j + 1u, count, first);
+                b200_counter_note(e2, head + 4u * j + 2u, count, first);
+                b200_counter_note(e3, head + 4u * j + 3u, count, first);
             }
         }
     }
-    /* words past the last whole vector (length % 16 != 0) and the first byte: one thread */
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (uint64_t w = n_vec * 4u; w < p.n_words; ++w)
-            b200_counter_note(b200_counter_diff(in[w], w + 1 < p.n_words ? in[w + 1] : (in[w] >> 24) + 1u), w, count, first);
-        if (p.expect_first >= 0 && p.n_words > 0 && (in[0] & 0xffu) != (uint32_t)p.expect_first) {
+    /* head words, words past the last whole vector, the first byte and the carried expectation: one thread */
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.n_words > 0) {
+        for (int part = 0; part < 2; ++part) {
+            const uint64_t lo = part ? head + n_vec * 4u : 0u, hi = part ? p.n_words : head;
+            for (uint64_t w = lo; w < hi; ++w)
+                b200_counter_note(b200_counter_diff(in0[w], w + 1 < p.n_words ? in0[w + 1] : (in0[w] >> 24) + 1u), w, count, first);
+        }
+        int32_t expect = p.expect_first;
+        if (p.stream) expect = p.stream->expect > 255u ? -1 : (int32_t)p.stream->expect;
+        if (expect >= 0 && (in0[0] & 0xffu) != (uint32_t)expect) {
             count += 1;
             first = 0;
         }
+        if (p.stream) p.stream->expect = ((in0[p.n_words - 1] >> 24) + 1u) & 0xffu;
     }
     if (__any_sync(0xffffffffu, first != ~0ull)) { /* rare: a clean stream never gets here */
         count = __reduce_add_sync(0xffffffffu, count);
@@ -133,8 +151,13 @@ __global__ void __launch_bounds__(256) k_counter_check(CounterParams p)
             if (other < first) first = other;
         }
         if (lane == 0) {
-            atomicAdd(p.n_breaks + c, (unsigned long long)count);
-            atomicMin(p.first_break + c, (unsigned long long)first);
+            if (p.stream) {
+                atomicAdd(&p.stream->n_breaks, (unsigned long long)count);
+                atomicMin(&p.stream->first_break, (unsigned long long)(p.pos_base + first));
+            } else {
+                atomicAdd(p.n_breaks + c, (unsigned long long)count);
+                atomicMin(p.first_break + c, (unsigned long long)first);
+            }
         }
     }
 }

@@ -338,6 +338,33 @@ def test_streaming_all_chains_block_cut_invariance(sdr_lib, g, cuts_kind, submit
     assert am.size == n_am and np.max(np.abs(am - gam[:n_am])) <= AM_AUDIO_ATOL
 
 
+@pytest.mark.parametrize("chains", ["counter_only", "all_chains"])
+@pytest.mark.parametrize("cuts_kind", ["baseline_blocks", "reference_512", "random"])
+def test_streaming_counter_check(sdr_lib, g, cuts_kind, chains):
+    """The firmware's own stream (test-mode counter) through process_samples: totals over the whole stream equal the
+    golden check of the concatenated bytes however the stream is cut -- also when a break falls on a block
+    boundary -- and the device stream buffer wraps several times on the way."""
+    total = 262144 * 9 + 512 * 3
+    u = (np.arange(total + 96) % 256).astype(np.uint8)
+    u = np.delete(u, np.r_[70000:70032, 262144:262176, 262144 * 5 + 508:262144 * 5 + 540])[:total]  # three drops of 32 bytes
+    u[262144 * 7 + 3] ^= 1                                                                         # one corrupted byte
+    want = g.counter_check(u)
+    assert want[0] == 5 and want[1] == 70000
+    cuts = {"baseline_blocks": [262144] * 9 + [512 * 3], "reference_512": [512] * (total // 512),
+            "random": random_cuts(total, 65536, 11)}[cuts_kind]
+    mask = sdr_lib.CHAIN_COUNTER if chains == "counter_only" else (sdr_lib.CHAIN_COUNTER | sdr_lib.CHAIN_SPECTRUM |
+                                                                   sdr_lib.CHAIN_WBFM | sdr_lib.CHAIN_AM)
+    with sdr_lib.B200Sdr(chains=mask, slot_bytes=262144, ring_slots=4) as s:
+        feed(s, u, cuts)
+        assert s.get_counter_check() == want
+        s.reset()                               # a new stream: totals and the carried byte start over
+        feed(s, u[:4096], [4096])
+        assert s.get_counter_check() == (0, None)
+    with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
+        with pytest.raises(sdr_lib.B200SdrError):
+            s.get_counter_check()
+
+
 def test_streaming_reset_starts_a_new_capture(sdr_lib, g):
     iq = g.synth(1, 262144, SYNTH_MULTITONE, 91)
     with sdr_lib.B200Sdr(chains=sdr_lib.CHAIN_SPECTRUM) as s:
