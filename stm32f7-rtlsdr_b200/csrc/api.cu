@@ -986,7 +986,7 @@ int32_t b200sdr_counter_check_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint3
             p.first_break = d_res + n_captures;
             const uint64_t n_vec = len_each / 16u;
             const uint64_t blocks = n_vec ? b200::ceil_div(n_vec, 1024) : 1;
-            if (blocks > 0x7fffffffull) return fail(ctx, B200SDR_NOT_SUPPORTED, "capture too long");
+            if (blocks > 0x3fffffull) return fail(ctx, B200SDR_NOT_SUPPORTED, "capture too long (the kernel indexes vectors with 32 bits)");
             k_counter_check<<<dim3((unsigned)blocks, n_captures), 256, 0, ctx->s_compute>>>(p);
             if ((e = cudaGetLastError()) != cudaSuccess) break;
             ctx->launches += 1;

@@ -50,10 +50,10 @@ __global__ void __launch_bounds__(256) k_convert_cf32(const uint32_t *__restrict
  * first one, per capture; the only HBM-bound chain of the path next to K2: 1 byte read per byte, nothing written.
  *   a break at index i (1 <= i < len)  <=>  u[i] != (u[i-1] + 1) & 0xff;  i = 0 breaks iff expect_first >= 0 and
  *   u[0] != expect_first (the value that continues the previous block).
- * A thread takes four 16-byte vectors 256 vectors apart (every warp load is 512 contiguous bytes); inside a
+ * A warp takes 128 consecutive 16-byte vectors as four loads of 512 contiguous bytes; inside a
  * word the four byte lanes are compared at once: s = the word shifted down one byte with the next word's first
  * byte on top (funnel shift) must equal the word with every byte incremented.  The next vector's first word comes
- * from the neighbouring lane (lane 31 reads it).  `n_vec` = capture length / 16, `n_words` = length / 4 (the tail of a
+ * from the neighbouring lane (lane 31: from lane 0 of the warp's next load).  `n_vec` = capture length / 16, `n_words` = length / 4 (the tail of a
  * length that is not a multiple of 16 is handled word by word by the last block). */
 struct CounterStreamState {      /* carried from block to block by the streaming path (one capture) */
     unsigned long long n_breaks, first_break; /* first_break: absolute byte index in the stream, ~0 = none */
@@ -102,29 +102,47 @@ __global__ void __launch_bounds__(256) k_counter_check(CounterParams p)
     const int lane = (int)(threadIdx.x & 31u);
     uint32_t count = 0;
     uint64_t first = ~0ull;
-    const uint64_t base = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
-    uint4 vv[4];
+    /* a warp owns 128 consecutive vectors (2 KB) as four 512-byte loads, so the successor of lane 31's vector is
+     * lane 0's vector of the warp's next load, and only the vector after the warp's last one is an extra
+     * (broadcast) read.  32-bit vector indices: the host keeps captures below 2^32 vectors. */
+    const uint32_t nv = (uint32_t)n_vec;
+    const uint32_t wbase = blockIdx.x * 1024u + (threadIdx.x >> 5) * 128u;
+    const uint4 *vec = reinterpret_cast<const uint4 *>(in);
+    if (wbase + 128u < nv) { /* warp-uniform: all 128 vectors and the one after them exist */
+        uint4 vv[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { /* all four loads in flight before the first use */
-        const uint64_t j = base + 256u * k;
-        vv[k] = j < n_vec ? __ldcs(reinterpret_cast<const uint4 *>(in) + j) : make_uint4(0u, 0u, 0u, 0u);
-    }
+        for (int k = 0; k < 4; ++k) vv[k] = __ldcs(vec + (wbase + 32u * k + lane)); /* all loads in flight first */
+        const uint32_t after = __ldg(in + (uint64_t)(wbase + 128u) * 4u);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint64_t j = base + 256u * k;
-        const uint4 v = vv[k];
-        /* first word of the next vector: the neighbouring lane has it; lane 31 and the last vector read it;
-         * the very last byte of a capture has no successor, so it is given the one it expects */
-        uint32_t next = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 31 || j + 1 >= n_vec) next = (j + 1) * 4u < rest ? __ldg(in + (j + 1) * 4u) : (v.w >> 24) + 1u;
-        if (j < n_vec) {
+        for (int k = 0; k < 4; ++k) {
+            const uint4 v = vv[k];
+            const uint32_t up = __shfl_down_sync(0xffffffffu, v.x, 1);
+            const uint32_t wrap = k < 3 ? __shfl_sync(0xffffffffu, vv[k < 3 ? k + 1 : 3].x, 0) : after;
+            const uint32_t next = lane == 31 ? wrap : up;
             const uint32_t e0 = b200_counter_diff(v.x, v.y), e1 = b200_counter_diff(v.y, v.z);
             const uint32_t e2 = b200_counter_diff(v.z, v.w), e3 = b200_counter_diff(v.w, next);
             if (e0 | e1 | e2 | e3) {
-                b200_counter_note(e0, head + 4u * j, count, first);
-                b200_counter_note(e1, head + 4u * j + 1u, count, first);
-                b200_counter_note(e2, head + 4u * j + 2u, count, first);
-                b200_counter_note(e3, head + 4u * j + 3u, count, first);
+                const uint64_t w0 = head + 4u * (uint64_t)(wbase + 32u * k + lane);
+                b200_counter_note(e0, w0, count, first);
+                b200_counter_note(e1, w0 + 1u, count, first);
+                b200_counter_note(e2, w0 + 2u, count, first);
+                b200_counter_note(e3, w0 + 3u, count, first);
+            }
+        }
+    } else if (wbase < nv) { /* the last warp(s) of a capture: bounds per vector */
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t j = (uint64_t)wbase + 32u * k + lane;
+            const uint4 v = j < n_vec ? __ldcs(vec + j) : make_uint4(0u, 0u, 0u, 0u);
+            /* the neighbouring lane has the next vector's first word; lane 31 and the last vector read it;
+             * the very last byte of a capture has no successor, so it is given the one it expects */
+            uint32_t next = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31 || j + 1 >= n_vec) next = (j + 1) * 4u < rest ? __ldg(in + (j + 1) * 4u) : (v.w >> 24) + 1u;
+            if (j < n_vec) {
+                b200_counter_note(b200_counter_diff(v.x, v.y), head + 4u * j, count, first);
+                b200_counter_note(b200_counter_diff(v.y, v.z), head + 4u * j + 1u, count, first);
+                b200_counter_note(b200_counter_diff(v.z, v.w), head + 4u * j + 2u, count, first);
+                b200_counter_note(b200_counter_diff(v.w, next), head + 4u * j + 3u, count, first);
             }
         }
     }
