@@ -207,6 +207,49 @@ static inline float __shfl_xor_sync(unsigned m, float v, int x)
     return r;
 }
 
+/* integer shuffles, votes and reductions (misc_kernels.cuh k_counter_check) */
+static inline uint32_t __shfl_sync(unsigned m, uint32_t v, int lane)
+{
+    (void)m;
+    return emu_shfl_raw(v, (emu::S().current & ~31) + (lane & 31));
+}
+static inline uint32_t __shfl_down_sync(unsigned m, uint32_t v, unsigned d)
+{
+    (void)m;
+    int me = emu::S().current, lane = me & 31;
+    return emu_shfl_raw(v, lane + (int)d < 32 ? me + (int)d : me);
+}
+static inline uint64_t __shfl_xor_sync(unsigned m, uint64_t v, int x)
+{
+    (void)m;
+    int src = (emu::S().current & ~31) | ((emu::S().current ^ x) & 31);
+    uint32_t lo = emu_shfl_raw((uint32_t)v, src), hi = emu_shfl_raw((uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+static inline uint32_t __reduce_add_sync(unsigned m, uint32_t v)
+{
+    (void)m;
+    emu::State &s = emu::S();
+    s.shfl_buf[s.current] = v;
+    emu::warp_barrier();
+    uint32_t r = 0;
+    for (int l = 0; l < 32; ++l) r += s.shfl_buf[(s.current & ~31) + l];
+    emu::warp_barrier();
+    return r;
+}
+static inline int __any_sync(unsigned m, int pred) { return __reduce_add_sync(m, pred ? 1u : 0u) != 0u; }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift)
+{
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (shift & 31));
+}
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
+static inline uint4 __ldcs(const uint4 *p) { return *p; }
+static inline unsigned __ldcs(const unsigned *p) { return *p; }
+static inline void __stcs(float4 *p, float4 v) { *p = v; }
+
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel)
 {
     uint64_t v = ((uint64_t)b << 32) | a;

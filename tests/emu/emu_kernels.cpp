@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../stm32f7-rtlsdr_b200/csrc/plan.h"
+#include "../../stm32f7-rtlsdr_b200/csrc/misc_kernels.cuh"
 
 extern "C" {
 
@@ -115,6 +116,29 @@ void emu_plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_coun
     out3[1] = pl.frames_per_warp;
     out3[2] = pl.ctas_per_capture;
 }
+
+/* K0 counter check over one capture starting at any 4-byte boundary; `state` (CounterStreamState, may be NULL)
+ * makes it a streaming step with absolute position pos_base, as stream_counter() in csrc/api.cu launches it */
+int emu_counter_check(const uint8_t *u, uint64_t len_bytes, int expect_first, uint64_t *n_breaks, uint64_t *first_break,
+                      void *state, uint64_t pos_base)
+{
+    unsigned long long res[2] = {0ull, ~0ull};
+    CounterParams p{};
+    p.in = (const uint32_t *)u;
+    p.n_words = len_bytes / 4u;
+    p.stride_words = p.n_words;
+    p.expect_first = expect_first;
+    p.n_breaks = &res[0];
+    p.first_break = &res[1];
+    p.stream = (CounterStreamState *)state;
+    p.pos_base = pos_base;
+    const uint32_t blocks = (uint32_t)b200::ceil_div(b200::ceil_div(p.n_words, 4), 1024);
+    emu::launch(dim3(blocks ? blocks : 1, 1), dim3(256), 0, [&] { k_counter_check(p); });
+    *n_breaks = res[0];
+    *first_break = res[1];
+    return (int)blocks;
+}
+int emu_sizeof_counter_state(void) { return (int)sizeof(CounterStreamState); }
 
 /* AM over whole captures: k_am_front (optionally segmented) + k_am_back */
 int emu_am_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, uint32_t tiles_per_segment,

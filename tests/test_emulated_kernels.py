@@ -60,6 +60,54 @@ def test_spectrum_launch_plan(emu):
     assert plan(48_000_000, 1, 74)[1] > plan(48_000_000, 1, 148)[1]   # fewer SMs -> longer warps
 
 
+def aligned_bytes(n, offset):
+    """n bytes starting `offset` bytes after a 64-byte boundary"""
+    raw = np.zeros(n + 128, np.uint8)
+    start = (-raw.ctypes.data) % 64 + offset
+    return raw[start:start + n]
+
+
+@pytest.mark.parametrize("nbytes,offset", [(4, 0), (12, 4), (16, 0), (20, 12), (2048 + 16, 0), (2048 + 32, 0), (2048 + 36, 8),
+                                           (16384, 0), (16384 + 2048 + 20, 4), (3 * 16384 + 2064, 0)])
+def test_counter_kernel_logic(emu, g, nbytes, offset):
+    """k_counter_check under the host emulation: warp-contiguous fast path, the bounds-checked last warps, head words
+    before the first 16-byte boundary, tail words, breaks on every kind of boundary, the streaming state."""
+    emu.emu_counter_check.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.c_void_p, C.c_uint64]
+
+    def run(u, expect=-1, state=None, pos_base=0):
+        n, f = C.c_uint64(0), C.c_uint64(0)
+        emu.emu_counter_check(u.ctypes.data, u.size, expect, C.byref(n), C.byref(f), state, pos_base)
+        return n.value, (None if f.value == 2**64 - 1 else f.value)
+
+    rng = np.random.default_rng(nbytes + offset)
+    u = aligned_bytes(nbytes, offset)
+    u[:] = (np.arange(nbytes) + 250) % 256
+    assert run(u) == (0, None) and run(u, 250) == (0, None) and run(u, 3) == (1, 0)
+    for _ in range(3):
+        v = aligned_bytes(nbytes, offset)
+        v[:] = u
+        where = [w for w in list(rng.integers(0, nbytes, size=4)) + [nbytes - 1, 3, 4, 15, 16, 511, 512, 2047, 2048, 2063, 16383, 16384]
+                 if w < nbytes]
+        v[where] = rng.integers(0, 256, size=len(where), dtype=np.uint8)
+        for expect in (-1, 250):
+            assert run(v, expect) == g.counter_check(v, expect)
+    # streaming: two consecutive blocks with a carried byte; totals carry absolute positions
+    if nbytes >= 16:
+        assert emu.emu_sizeof_counter_state() == 24
+        st = np.zeros(3, np.uint64)
+        st[1], st[2] = 2**64 - 1, 0xFFFFFFFF   # n_breaks = 0, first_break = none, expect = unknown
+        cut = (nbytes // 2) & ~3
+        a, b = aligned_bytes(cut, offset), aligned_bytes(nbytes - cut, (offset + cut) % 16)
+        whole = u.copy()
+        whole[cut] ^= 0x10                      # a break exactly on the block boundary (and the byte after it)
+        a[:], b[:] = whole[:cut], whole[cut:]
+        run(a, state=st.ctypes.data, pos_base=0)
+        run(b, state=st.ctypes.data, pos_base=cut)
+        want = g.counter_check(whole)
+        assert (int(st[0]), int(st[1])) == (want[0], want[1]) and int(st[2]) & 0xFFFFFFFF == (int(whole[-1]) + 1) % 256
+
+
 @pytest.mark.parametrize("frames_per_warp,window", [(1, WIN_HANN), (3, WIN_HANN), (8, WIN_BLACKMAN)])
 def test_spectrum_kernel_logic(emu, g, frames_per_warp, window):
     n = 512 * 21 + 1024 + 100
