@@ -33,6 +33,14 @@ SCRIPT = textwrap.dedent("""
         s.lib.b200sdr_copy_to_dev(s.ctx, d_in, iq.ctypes.data, 65536)
         s.split_spectrum_dev(d_in, 65536, 63, d_out); s.exchange_wait()
         s.dev_free(d_in); s.dev_free(d_out)
+        # K0: ragged host block (head / tail words, last warps), then live blocks starting on odd word boundaries
+        cnt = (np.arange(16384 + 2048 + 20) %% 256).astype(np.uint8)
+        cnt[5000] ^= 1
+        assert s.counter_check(cnt, 0)[0] == 2
+    with pkg.B200Sdr(chains=pkg.CHAIN_COUNTER, slot_bytes=65024, ring_slots=3, submit_bytes=4) as c:
+        for off in range(0, 4 * 4100, 4100):
+            c.process_samples(cnt[off:off + 4100])
+        assert c.get_counter_check()[0] == 2
     print("SANITIZED_RUN_OK")
 """) % ROOT
 
