@@ -117,6 +117,24 @@ void emu_plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_coun
     out3[2] = pl.ctas_per_capture;
 }
 
+/* K2 conversion (window may be NULL) as b200sdr_convert_cf32_dev launches it; len_bytes % 16 == 0 */
+int emu_convert_cf32(const uint8_t *iq, uint64_t len_bytes, const float *window, float *out)
+{
+    const uint64_t n_words = len_bytes / 4;
+    emu::launch(dim3((unsigned)((n_words + 1023) / 1024), 1), dim3(256), 0,
+                [&] { k_convert_cf32((const uint32_t *)iq, (float4 *)out, n_words, window); });
+    return 0;
+}
+
+/* the device generator of the synthetic captures as b200sdr_synth_fill_dev launches it; `lut` = the sine table */
+int emu_synth(uint8_t *out, uint32_t n_captures, uint64_t len_each, uint32_t kind, uint64_t first_capture, const float *lut)
+{
+    const uint64_t groups = len_each / 16;
+    emu::launch(dim3((unsigned)((groups + 255) / 256), n_captures), dim3(256), 0,
+                [&] { k_synth((uint4 *)out, groups, groups, kind, first_capture, lut); });
+    return 0;
+}
+
 /* K0 counter check over one capture starting at any 4-byte boundary; `state` (CounterStreamState, may be NULL)
  * makes it a streaming step with absolute position pos_base, as stream_counter() in csrc/api.cu launches it */
 int emu_counter_check(const uint8_t *u, uint64_t len_bytes, int expect_first, uint64_t *n_breaks, uint64_t *first_break,

@@ -60,6 +60,28 @@ def test_spectrum_launch_plan(emu):
     assert plan(48_000_000, 1, 74)[1] > plan(48_000_000, 1, 148)[1]   # fewer SMs -> longer warps
 
 
+def test_convert_and_generator_kernels(emu, g):
+    """k_convert_cf32 (bit-exact, with and without a window) and k_synth (bytes identical to the host generator that
+    the oracle shares through include/b200sdr_synth.h) under the host emulation."""
+    emu.emu_convert_cf32.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    emu.emu_synth.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p]
+    iq = np.random.default_rng(3).integers(0, 256, 16 * 1500 + 16 * 3, dtype=np.uint8)
+    iq[:256] = np.arange(256)                       # every byte value
+    out = np.full(iq.size, np.nan, np.float32)
+    emu.emu_convert_cf32(iq.ctypes.data, iq.size, None, out.ctypes.data)
+    assert np.array_equal(out.astype(np.float64), g.convert(iq))
+    w = g.window(WIN_HANN).astype(np.float32)
+    emu.emu_convert_cf32(iq.ctypes.data, iq.size, w.ctypes.data, out.ctypes.data)
+    want = (g.convert(iq).astype(np.float32) * np.repeat(np.resize(w, iq.size // 2), 2)).astype(np.float32)
+    assert np.array_equal(out, want)                # one rounded fp32 multiply by the fp32 window value
+    lut = np.sin(2 * np.pi * (np.arange(4097) % 4096) / 4096).astype(np.float32)
+    for kind in (SYNTH_MULTITONE, SYNTH_WBFM, SYNTH_AM, 0):
+        n_cap, len_each = 2, 16 * 300
+        buf = np.zeros(n_cap * len_each, np.uint8)
+        emu.emu_synth(buf.ctypes.data, n_cap, len_each, kind, 5, lut.ctypes.data)
+        assert np.array_equal(buf, g.synth(n_cap, len_each, kind, 5))
+
+
 def aligned_bytes(n, offset):
     """n bytes starting `offset` bytes after a 64-byte boundary"""
     raw = np.zeros(n + 128, np.uint8)
