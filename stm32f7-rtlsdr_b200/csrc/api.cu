@@ -450,8 +450,7 @@ int slot_ready(b200sdr_ctx *ctx, uint32_t slot)
 int upload_thresholds(b200sdr_ctx *ctx, float db_min, float db_max)
 {
     float thr[B200_LCD_H];
-    for (int h = 0; h < B200_LCD_H; ++h)
-        thr[h] = (float)pow(10.0, ((double)db_min + ((double)db_max - (double)db_min) * (double)h / (B200_LCD_H - 1.0)) / 10.0);
+    b200_fill_thresholds(thr, db_min, db_max);
     if (!ctx->d_thresholds) CU(cudaMalloc((void **)&ctx->d_thresholds, sizeof thr));
     CU(cudaMemcpyAsync(ctx->d_thresholds, thr, sizeof thr, cudaMemcpyHostToDevice, ctx->s_compute));
     CU(cudaStreamSynchronize(ctx->s_compute)); /* `thr` is a stack buffer */

@@ -38,6 +38,15 @@ B200_HD uint32_t b200_ramp_argb(int y) /* y = height above the bottom row, 0..27
     return 0xFF000000u | ((uint32_t)r << 16) | ((uint32_t)g << 8) | (uint32_t)b;
 }
 
+/* host side: dB thresholds of the 272 LCD rows, T[h] = 10^((db_min + (db_max - db_min) h / 271) / 10), computed in
+ * double and rounded once (shared by the C ABI and the test-suite's host emulation of the kernels) */
+#include <math.h>
+static inline void b200_fill_thresholds(float *thr272, float db_min, float db_max) /* host function */
+{
+    for (int h = 0; h < B200_LCD_H; ++h)
+        thr272[h] = (float)pow(10.0, ((double)db_min + ((double)db_max - (double)db_min) * (double)h / (B200_LCD_H - 1.0)) / 10.0);
+}
+
 /* one CTA of 480 threads per spectrum; `scale` multiplies the stored values first (1/frames for
  * the streaming accumulator, which holds the sum) */
 __global__ void __launch_bounds__(B200_LCD_W) k_render_spectrum(const float *__restrict__ spectra, float scale,

@@ -11,6 +11,7 @@
 
 #include "../../stm32f7-rtlsdr_b200/csrc/plan.h"
 #include "../../stm32f7-rtlsdr_b200/csrc/misc_kernels.cuh"
+#include "../../stm32f7-rtlsdr_b200/csrc/render.cuh"
 
 extern "C" {
 
@@ -132,6 +133,22 @@ int emu_synth(uint8_t *out, uint32_t n_captures, uint64_t len_each, uint32_t kin
     const uint64_t groups = len_each / 16;
     emu::launch(dim3((unsigned)((groups + 255) / 256), n_captures), dim3(256), 0,
                 [&] { k_synth((uint4 *)out, groups, groups, kind, first_capture, lut); });
+    return 0;
+}
+
+/* presentation kernels as b200sdr_render_spectrum_dev / b200sdr_render_waterfall_dev launch them */
+int emu_render_spectrum(const float *spectra, uint32_t n_spectra, float scale, float db_min, float db_max, uint32_t *argb)
+{
+    float thr[B200_LCD_H];
+    b200_fill_thresholds(thr, db_min, db_max);
+    emu::launch(dim3(n_spectra), dim3(B200_LCD_W), 0, [&] { k_render_spectrum(spectra, scale, thr, argb); });
+    return 0;
+}
+int emu_render_waterfall(const float *spectra, uint32_t n_rows, float scale, float db_min, float db_max, uint32_t *argb)
+{
+    float thr[B200_LCD_H];
+    b200_fill_thresholds(thr, db_min, db_max);
+    emu::launch(dim3(B200_LCD_H), dim3(B200_LCD_W), 0, [&] { k_render_waterfall(spectra, n_rows, scale, thr, argb); });
     return 0;
 }
 

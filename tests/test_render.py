@@ -40,6 +40,28 @@ def test_golden_render_geometry_and_colours():
         assert not np.any(col[:-1] & ~col[1:])
 
 
+def test_render_kernels_under_host_emulation():
+    """k_render_spectrum / k_render_waterfall source on the host (tests/emu): bit-exact images without a GPU."""
+    g = Golden()
+    emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "libemu_kernels.so"))  # built by conftest.py
+    emu.emu_render_spectrum.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    emu.emu_render_waterfall.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(1)
+    spectra = (np.abs(rng.standard_normal((3, 1024))) * 10.0 ** rng.uniform(0, 9, (3, 1024))).astype(np.float32)
+    for db_min, db_max in ((0.0, 100.0), (20.0, 90.0)):
+        img = np.zeros((3, 272, 480), np.uint32)
+        emu.emu_render_spectrum(spectra.ctypes.data, 3, 1.0, db_min, db_max, img.ctypes.data)
+        for k in range(3):
+            assert np.array_equal(img[k], gold_render(g, spectra[k], db_min, db_max))
+        wf = np.zeros((272, 480), np.uint32)
+        emu.emu_render_waterfall(spectra.ctypes.data, 3, 1.0, db_min, db_max, wf.ctypes.data)
+        assert np.array_equal(wf, gold_waterfall(g, spectra, db_min, db_max))
+    # the streaming accumulator holds sums: the kernel applies 1/frames with one rounded multiply
+    img = np.zeros((1, 272, 480), np.uint32)
+    emu.emu_render_spectrum(spectra.ctypes.data, 1, np.float32(1.0 / 255), 0.0, 100.0, img.ctypes.data)
+    assert np.array_equal(img[0], gold_render(g, spectra[0] * np.float32(1.0 / 255), 0.0, 100.0))
+
+
 @pytest.mark.gpu
 def test_render_bit_exact_against_golden(sdr_lib):
     g = Golden()
