@@ -121,6 +121,8 @@ static struct ref_ctl_rec *g_trace;
 static uint32_t g_trace_cap, g_trace_n;
 static uint16_t g_i2c_last_addr;
 static uint8_t g_i2c_last_reg;
+static uint8_t g_e4k_regs[256]; /* E4000 register file: a write of (reg, val) stores, a write of (reg) selects, a read returns */
+static int g_full_tuner;        /* 1: keep the reference's own E4000 driver in the loop (ref_init_trace_full) */
 static uint8_t ref_trace_step(void);
 USBH_StatusTypeDef USBH_CtlReq(USBH_HandleTypeDef *phost, uint8_t *buff, uint16_t length)
 {
@@ -129,12 +131,12 @@ USBH_StatusTypeDef USBH_CtlReq(USBH_HandleTypeDef *phost, uint8_t *buff, uint16_
     const int in = (su->b.bmRequestType & 0x80) != 0;
     if (in) {
         memset(buff, 0, length);
-        if (su->b.wIndex.w == (IICB << 8) && su->b.wValue.w == E4K_I2C_ADDR && g_i2c_last_addr == E4K_I2C_ADDR &&
-            g_i2c_last_reg == E4K_CHECK_ADDR && length >= 1)
-            buff[0] = E4K_CHECK_VAL;
+        if (su->b.wIndex.w == (IICB << 8) && su->b.wValue.w == E4K_I2C_ADDR && g_i2c_last_addr == E4K_I2C_ADDR && length >= 1)
+            buff[0] = g_i2c_last_reg == E4K_CHECK_ADDR ? E4K_CHECK_VAL : g_e4k_regs[g_i2c_last_reg];
     } else if (su->b.wIndex.w == ((IICB << 8) | 0x10) && length >= 1) {
         g_i2c_last_addr = su->b.wValue.w;
         g_i2c_last_reg = buff[0];
+        if (su->b.wValue.w == E4K_I2C_ADDR && length >= 2) g_e4k_regs[buff[0]] = buff[1];
     }
     if (g_trace_n < g_trace_cap) {
         struct ref_ctl_rec *r = &g_trace[g_trace_n];
@@ -369,7 +371,8 @@ uint32_t ref_e4k_pll(uint32_t fosc, uint32_t intended_flo, uint32_t out8[8])
  * USBH_Process does (usbh_core.c:557), polled until it reports the class active.  Every control transfer it
  * issues is recorded by USBH_CtlReq above.  The E4000 driver's own init (steps 28, 29 and the SetBW call
  * inside RTLSDR_set_sample_rate) is a separate state machine over dozens of I2C registers; it is replaced by
- * a tuner that accepts everything, after the reference's probe has found "its" E4000.
+ * a tuner that accepts everything, after the reference's probe has found "its" E4000 (ref_init_trace_full keeps
+ * the reference's driver instead, against a register-file model of the chip).
  * Returns the number of transfers (which may exceed cap), or < 0.
  * ------------------------------------------------------------------------------------------- */
 static USBH_StatusTypeDef tuner_ok(USBH_HandleTypeDef *phost) { (void)phost; return USBH_OK; }
@@ -391,9 +394,10 @@ long ref_init_trace(uint8_t *out, uint32_t cap_records)
     g_trace_n = 0;
     g_i2c_last_addr = 0;
     g_i2c_last_reg = 0;
+    memset(g_e4k_regs, 0, sizeof g_e4k_regs);
     long rc = -2;
-    for (int polls = 0; polls < 100000; ++polls) {
-        if (handle()->reqNumber == 28 && handle()->tuner == &Tuner_E4K) handle()->tuner = &g_null_tuner;
+    for (int polls = 0; polls < 400000; ++polls) {
+        if (!g_full_tuner && handle()->reqNumber == 28 && handle()->tuner == &Tuner_E4K) handle()->tuner = &g_null_tuner;
         USBH_StatusTypeDef st = g_host.pActiveClass->Requests(&g_host);
         if (st == USBH_OK) { rc = (long)g_trace_n; break; }
         /* anything else means "call me again": USBH_Process only looks for USBH_OK (usbh_core.c:557-562), and the
@@ -403,9 +407,30 @@ long ref_init_trace(uint8_t *out, uint32_t cap_records)
     return rc;
 }
 
+/* the same with the reference's own E4000 driver left in (steps 28, 29, SetBW): does its init FSM terminate against
+ * a plain register-file model of the chip, and what does it put on the wire? */
+long ref_init_trace_full(uint8_t *out, uint32_t cap_records)
+{
+    g_full_tuner = 1;
+    long n = ref_init_trace(out, cap_records);
+    g_full_tuner = 0;
+    return n;
+}
+
 #ifdef REF_CLI
 static int cli_frontend(int argc, char **argv)
 {
+    if (strcmp(argv[1], "--init-trace-full") == 0 && argc >= 3) {
+        static uint8_t buf[12 * 8192];
+        long n = ref_init_trace_full(buf, 8192);
+        printf("REF_INIT_TRACE_FULL %ld step=%u\n", n, (unsigned)handle()->reqNumber);
+        if (n < 0 || n > 8192) return 1;
+        FILE *f = fopen(argv[2], "wb");
+        if (!f) return 1;
+        fwrite(buf, 12, (size_t)n, f);
+        fclose(f);
+        return 0;
+    }
     if (strcmp(argv[1], "--init-trace") == 0 && argc >= 3) { /* writes the 12-byte records to argv[2] */
         static uint8_t buf[12 * 4096];
         long n = ref_init_trace(buf, 4096);

@@ -178,3 +178,19 @@ def test_init_sequence_bit_exact_against_reference(b, tmp_path):
     rc, n, got = b.rtl_init_sequence(240000, flags=1)
     assert rc == 0 and n == 108
     assert got == want
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+def test_init_sequence_with_the_reference_tuner_driver_in_the_loop(b, tmp_path):
+    """Same recording, but with the reference's own E4000 driver left in (Init, InitProcess, SetBW against a plain
+    register-file model of the chip): its 70 I2C transfers land exactly where the product's list leaves room for
+    the tuner (steps 29 and 30), and everything else is still the product's list, transfer for transfer."""
+    path = str(tmp_path / "full.bin")
+    assert ref("--init-trace-full", path)[0] == "178"
+    dt = np.dtype([("t", "u1"), ("r", "u1"), ("v", "<u2"), ("i", "<u2"), ("l", "<u2"), ("d", "u1", 2), ("step", "u1"), ("pad", "u1")])
+    full = np.fromfile(path, dt)
+    tuner_i2c = np.flatnonzero(((full["i"] == 0x0610) | (full["i"] == 0x0600)) & (full["v"] == 0xC8))[2:]  # after the probe pair
+    assert tuner_i2c.size == 70 and set(full["step"][tuner_i2c]) == {29, 30}
+    keep = np.ones(full.size, bool)
+    keep[tuner_i2c] = False
+    assert full[keep].tobytes() == b.rtl_init_sequence(240000, flags=1)[2]
