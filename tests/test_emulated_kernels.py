@@ -130,6 +130,31 @@ def test_counter_kernel_logic(emu, g, nbytes, offset):
         assert (int(st[0]), int(st[1])) == (want[0], want[1]) and int(st[2]) & 0xFFFFFFFF == (int(whole[-1]) + 1) % 256
 
 
+def test_counter_kernel_random_streams(emu, g):
+    """property check (hypothesis): any length, any 4-byte start alignment, any set of corrupted bytes, any first-byte
+    expectation -- the emulated kernel and the golden definition agree."""
+    from hypothesis import given, settings, strategies as st
+
+    emu.emu_counter_check.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                      C.c_void_p, C.c_uint64]
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 1400), st.integers(0, 3), st.integers(0, 255), st.lists(st.integers(0, 5599), max_size=6),
+           st.integers(-1, 255), st.integers(0, 2**32))
+    def check(words, off_words, start, hits, expect, seed):
+        n = 4 * words
+        u = aligned_bytes(n, 4 * off_words)
+        u[:] = (np.arange(n) + start) % 256
+        rng = np.random.default_rng(seed)
+        for h in hits:
+            u[h % n] = rng.integers(0, 256)
+        cnt, first = C.c_uint64(0), C.c_uint64(0)
+        emu.emu_counter_check(u.ctypes.data, n, expect, C.byref(cnt), C.byref(first), None, 0)
+        assert (cnt.value, None if first.value == 2**64 - 1 else first.value) == g.counter_check(u, expect)
+
+    check()
+
+
 @pytest.mark.parametrize("frames_per_warp,window", [(1, WIN_HANN), (3, WIN_HANN), (8, WIN_BLACKMAN)])
 def test_spectrum_kernel_logic(emu, g, frames_per_warp, window):
     n = 512 * 21 + 1024 + 100

@@ -194,3 +194,24 @@ def test_init_sequence_with_the_reference_tuner_driver_in_the_loop(b, tmp_path):
     keep = np.ones(full.size, bool)
     keep[tuner_i2c] = False
     assert full[keep].tobytes() == b.rtl_init_sequence(240000, flags=1)[2]
+
+
+def test_fir_pack_round_trip_property(b):
+    """property check (hypothesis): unpacking the 20 register bytes (8 x int8, then 4 x two int12 in three bytes) gives
+    back every in-range coefficient set."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(-128, 127), min_size=8, max_size=8), st.lists(st.integers(-2048, 2047), min_size=8, max_size=8))
+    def check(c8, c12):
+        rc, packed, _ = b.rtl_fir_pack(c8 + c12)
+        assert rc == 0 and len(packed) == 20
+        got8 = [v - 256 if v > 127 else v for v in packed[:8]]
+        got12 = []
+        for k in range(4):
+            b0, b1, b2 = packed[8 + 3 * k: 11 + 3 * k]
+            for v in ((b0 << 4) | (b1 >> 4), ((b1 & 0x0F) << 8) | b2):
+                got12.append(v - 4096 if v > 2047 else v)
+        assert got8 == c8 and got12 == c12
+
+    check()
