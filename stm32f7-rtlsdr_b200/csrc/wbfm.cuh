@@ -13,7 +13,9 @@
  * single buffer that is re-armed as soon as the FIR has consumed it (4 CTAs per SM overlap the rest).
  *
  * Stage 1 is written "input-partitioned": thread t owns input samples [a, a+120), a = tile + 120 t,
- * converts each byte pair exactly once (PRMT + one packed FADD) and scatters it into the (at most
+ * turns each byte pair into a pair of floats exactly once -- two PRMTs and no arithmetic: the bytes are read
+ * as raw (sub)normal floats u * 2^-133 and the -127.5 offset is carried by the accumulators' start values,
+ * cplx2.cuh form C -- and scatters it into the (at most
  * 8) outputs y1[m] = sum_k h[k] x[10 m - k] whose window covers it.  Eight packed accumulators
  * rotate; output i of the chunk (centre a + 10 i) completes at sample 10 i:
  *     i = 0..7   partially complete ("heads", started in the previous thread's chunk)
@@ -21,8 +23,9 @@
  *     i = 12..19 started here, finished by the next thread  ("tails", 8 partial sums)
  * Thread t+1 adds thread t's tails to its heads through shared memory; the last thread's tails
  * are carried to the next tile.  So the FIR needs NO input history at all -- a capture (or a
- * stream) starts with zero tails, which is exactly x[n<0] = 0 -- and costs exactly 8 packed FMAs
- * per input sample with taps held in registers (40 distinct: the filter is symmetric).
+ * stream) starts with the start-of-stream tails (FmTaps::bias_head), which is exactly x[n<0] = 0 -- and
+ * costs exactly 8 packed FMAs per input sample with taps held in registers (40 distinct: the filter is
+ * symmetric).
  *
  * The 240 kS/s stages run per tile on the 1536 fresh outputs: discriminator (atan2 of
  * y[m] conj(y[m-1])), the de-emphasis recurrence as a fixed-shape scan (thread-serial over 12,
