@@ -91,57 +91,112 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(B, world):
+    """The `config` object of BOTH arms (the GPU arm runs it whole; the CPU arm runs a bounded sample of it)."""
+    return {"workload": "configs[4] per-GPU share (= configs[1] spectrum + configs[2] WBFM on every capture): "
+                        f"{B} x 10 s captures (48 MB u8 I/Q each) per GPU, both chains per step",
+            "captures_per_gpu": B, "capture_seconds": 10, "sample_rate": 2.4e6, "nfft": 1024, "hop": 512,
+            "window": "hann", "cache": f"inputs {B * CAPTURE_BYTES / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
+            "parallelism": f"captures sharded over {world} GPU(s), no collective"}
+
+
+def load_traffic_ratio():
+    """DRAM bytes (read + write) per algorithmic byte of k_spectrum, from the newest tracked ncu capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic): never a literal in this file."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))["k_spectrum"]
+        return float(d["dram_bytes"]) / float(d["algorithmic_bytes"]), d.get("source", p)
+    except (OSError, KeyError, ValueError, ZeroDivisionError):
+        return None, None
+
+
 # ------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(threads, target_seconds):
-    """oracle/golden.c (fp32 build) on the host cores: each thread takes whole 1 s captures
-    (2.4 M complex samples) through the word-granular ingest copy + spectrum and + WBFM."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    from oracle_api import Golden, SYNTH_WBFM
-    g = Golden(f32=True)
-    # the ingest copy is the one part of the path the reference implements: time ITS code when
-    # the reference build (oracle/_ref, made from /root/reference by oracle/Makefile) is present
-    copy_impl = "restated USB_ReadPacket (oracle/golden.c)"
-    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_ingest.so")
-    if os.path.exists(ref_so):
-        ref = C.CDLL(ref_so)
-        g.lib.gold_set_ingest_hook.argtypes = [C.c_void_p]
-        g.lib.gold_set_ingest_hook(C.cast(ref.ref_copy_block, C.c_void_p))
-        g._ref_keepalive = ref
-        copy_impl = "the reference's own USB_ReadPacket (oracle/_ref)"
-    n_each = 2_400_000
-    probe = g.synth(1, 2 * n_each, SYNTH_WBFM, 0)
-    t1 = g.lib.gold_time_spectrum(probe.ctypes.data, n_each, 1, 1, 1)
-    t1 += g.lib.gold_time_wbfm(probe.ctypes.data, n_each, 1, 1, 1)
-    per_thread = max(1, int(round(target_seconds / max(t1, 1e-3))))
-    n_blocks = threads * per_thread
-    distinct = min(n_blocks, max(8, threads))     # distinct 4.8 MB buffers, visited round-robin
-    data = g.synth(distinct, 2 * n_each, SYNTH_WBFM, 0)
-    ts = g.lib.gold_time_spectrum(data.ctypes.data, n_each, distinct, n_blocks, threads)
-    tf = g.lib.gold_time_wbfm(data.ctypes.data, n_each, distinct, n_blocks, threads)
-    samples = n_blocks * n_each
-    return {"value": samples / (ts + tf) / 1e6, "unit": "MS/s", "cores": threads, "kind": "port",
-            "sample": f"{n_blocks} x 1 s captures (2.4 M samples each) through ingest copy [{copy_impl}] + spectrum + WBFM [oracle/golden.c fp32 build], {threads} threads",
-            "spectrum_MSps": samples / ts / 1e6, "wbfm_MSps": samples / tf / 1e6, "seconds": ts + tf}
+class CpuArm:
+    """oracle/golden.c (fp32 build) on the host cores, behind the word-granular ingest copy -- executed by the
+    reference's OWN USB_ReadPacket (oracle/_ref, HAL_Driver/Src/stm32f7xx_ll_usb.c:792-803) when that build is
+    present.  Checker / baseline only: nothing here is on the product path."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        import oracle_api
+        self.api = oracle_api
+        self.g = oracle_api.Golden(f32=True)
+        self.copy_impl = "restated USB_ReadPacket (oracle/golden.c)"
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_ingest.so")
+        if os.path.exists(ref_so):
+            ref = C.CDLL(ref_so)
+            self.g.lib.gold_set_ingest_hook.argtypes = [C.c_void_p]
+            self.g.lib.gold_set_ingest_hook(C.cast(ref.ref_copy_block, C.c_void_p))
+            self._ref_keepalive = ref
+            self.copy_impl = "the reference's own USB_ReadPacket (oracle/_ref)"
+        self._captures = None
+
+    def captures(self, distinct):
+        """`distinct` synthetic 10 s captures (even: multitone, odd: FM -- the GPU arm's mix), made once."""
+        if self._captures is None or self._captures[0] < distinct:
+            parts = [self.g.synth(1, CAPTURE_BYTES, self.api.SYNTH_MULTITONE if c % 2 == 0 else self.api.SYNTH_WBFM, c)
+                     for c in range(distinct)]
+            self._captures = (distinct, np.concatenate(parts))
+        return self._captures[1]
+
+    def step(self, threads, captures_per_thread=1):
+        """One bounded sample of the workload: threads x captures_per_thread 10 s captures, each through ingest copy +
+        spectrum and ingest copy + WBFM.  Returns (samples, seconds of timed compute, spectrum s, wbfm s)."""
+        n_blocks = threads * captures_per_thread
+        distinct = min(n_blocks, 8)
+        data = self.captures(distinct)
+        ts = self.g.lib.gold_time_spectrum(data.ctypes.data, CAPTURE_SAMPLES, distinct, n_blocks, threads)
+        tf = self.g.lib.gold_time_wbfm(data.ctypes.data, CAPTURE_SAMPLES, distinct, n_blocks, threads)
+        return n_blocks * CAPTURE_SAMPLES, ts + tf, ts, tf
+
+    def baseline(self, threads, target_seconds):
+        samples, sec, ts, tf = self.step(threads, 1)
+        reps = 1
+        while sec < target_seconds * 0.5 and reps < 8:        # fast hosts: a second, larger sample
+            reps *= 2
+            samples, sec, ts, tf = self.step(threads, reps)
+        return {"value": samples / sec / 1e6, "unit": "MS/s", "cores": threads, "kind": "port",
+                "sample": f"{threads * reps} x 10 s captures (24 M samples each, the GPU arm's capture length) through ingest copy "
+                          f"[{self.copy_impl}] + spectrum + WBFM [oracle/golden.c fp32 build], {threads} threads",
+                "spectrum_MSps": samples / ts / 1e6, "wbfm_MSps": samples / tf / 1e6, "seconds": sec}
+
+    def config0(self, threads_all):
+        """BASELINE.md section 3 / configs[0]: ONE 262 144-byte block -> ingest copy -> cf32 -> Hann -> 1024-pt FFT ->
+        |X|^2 -> mean of 255 frames; 1024 repetitions over 128 distinct buffers; 1 thread and all cores."""
+        blk, distinct, reps = 262144, 128, 1024
+        data = self.g.synth(distinct, blk, self.api.SYNTH_MULTITONE, 0)
+        out = {"block_bytes": blk, "repetitions": reps, "distinct_buffers": distinct, "nproc": threads_all,
+               "what": "configs[0]: one 256 KiB block -> ingest copy -> cf32 + 1024-pt Hann FFT power spectrum (255 frames), fp32 golden"}
+        for label, th in (("1_thread", 1), ("all_cores", threads_all)):
+            t = self.g.lib.gold_time_spectrum(data.ctypes.data, blk // 2, distinct, reps, th)
+            out[label] = {"threads": th, "MSps": reps * (blk // 2) / t / 1e6, "us_per_block": t / reps * 1e6}
+        return out
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals = []
+    arm = CpuArm()
+    arm.captures(min(threads, 8))                 # synthesis is not part of any timed step
     for _ in range(args.warmup):
-        cpu_reference(threads, 1.0)
-    t0 = time.time()
+        arm.step(threads, 1)
+    samples = sec = ts = tf = 0.0
     for _ in range(args.steps):
-        vals.append(cpu_reference(threads, float(os.environ.get("B200_REF_SECONDS", max(2.0, 20.0 / max(args.steps, 1))))))
-    res = vals[-1]
-    v = float(np.mean([x["value"] for x in vals]))
-    res["value"] = v
+        n, s_, a_, b_ = arm.step(threads, 1)
+        samples += n; sec += s_; ts += a_; tf += b_
+    v = samples / sec / 1e6
+    res = {"value": v, "unit": "MS/s", "cores": threads, "kind": "port",
+           "sample": f"each step = {threads} x 10 s captures (24 M samples each) through ingest copy [{arm.copy_impl}] + spectrum + "
+                     f"WBFM [oracle/golden.c fp32 build], {threads} threads; {args.steps} steps",
+           "spectrum_MSps": samples / ts / 1e6, "wbfm_MSps": samples / tf / 1e6, "seconds": sec,
+           "config0": arm.config0(threads)}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * (time.time() - t0) / max(args.steps, 1), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[4] share: 10 s captures through spectrum + WBFM (CPU arm: bounded sample of 1 s captures)"},
+            "config": workload_config(args.captures_per_gpu, world),
             "cpu_baseline": res, "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -245,6 +300,8 @@ def main():
     ap.add_argument("--captures-per-gpu", type=int, default=512)
     ap.add_argument("--e2e-captures", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-captures", type=int, default=64, help="captures per rank recomputed one at a time (bitwise check)")
+    ap.add_argument("--config4-waves", type=int, default=8, help="N=1 only: waves of captures-per-gpu captures (8 x 512 = configs[4]); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -378,6 +435,70 @@ def main():
     am_bytes = 2.0 + 4.0 * 8000.0 / 2400000.0
     am_gbs = am_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e9
 
+    # ---- parity of the sharded batch: every capture of this rank's shard recomputed ONE AT A TIME must
+    # give bitwise the spectrum / audio it got inside the batch of B (the summation tree follows from the capture
+    # length only, csrc/plan.h), and a capture computed on every GPU must give the same bits on every GPU.
+    step(3)
+    sdr.sync()
+    one_spec = torch.empty(1024, dtype=torch.float32, device="cuda")
+    one_audio = torch.empty(n_audio, dtype=torch.float32, device="cuda")
+    spec2, audio2 = spec.view(B, 1024), audio.view(B, n_audio)
+    n_checked, n_equal = 0, 0
+    for c in range(0, B, max(1, B // max(1, args.parity_captures))):
+        sdr.batch_spectrum_dev(iq.data_ptr() + c * CAPTURE_BYTES, 1, CAPTURE_BYTES, one_spec.data_ptr())
+        sdr.batch_wbfm_dev(iq.data_ptr() + c * CAPTURE_BYTES, 1, CAPTURE_BYTES, one_audio.data_ptr())
+        sdr.sync()
+        n_checked += 1
+        n_equal += int(torch.equal(one_spec, spec2[c]) and torch.equal(one_audio, audio2[c]))
+    # the job's capture 0 and 1 (multitone, FM) recomputed on EVERY rank: digests must agree across GPUs and across N
+    probe = torch.empty(2 * CAPTURE_BYTES, dtype=torch.uint8, device="cuda")
+    sdr.synth_fill_dev(probe.data_ptr(), 1, CAPTURE_BYTES, pkg.SYNTH_MULTITONE, first_capture=0)
+    sdr.synth_fill_dev(probe.data_ptr() + CAPTURE_BYTES, 1, CAPTURE_BYTES, pkg.SYNTH_WBFM, first_capture=1)
+    p_spec = torch.empty(2 * 1024, dtype=torch.float32, device="cuda")
+    p_audio = torch.empty(2 * n_audio, dtype=torch.float32, device="cuda")
+    sdr.batch_spectrum_dev(probe.data_ptr(), 2, CAPTURE_BYTES, p_spec.data_ptr())
+    sdr.batch_wbfm_dev(probe.data_ptr(), 2, CAPTURE_BYTES, p_audio.data_ptr())
+    sdr.sync()
+    import hashlib
+    digest = hashlib.sha256(p_spec.cpu().numpy().tobytes() + p_audio.cpu().numpy().tobytes()).hexdigest()[:16]
+    del probe
+    counts = torch.tensor([n_checked, n_equal], dtype=torch.int64, device="cuda")
+    digests = [digest]
+    if world > 1:
+        dist.all_reduce(counts)
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+    if rank == 0 and B >= 2:   # rank 0 owns the job's captures 0 and 1: the probe must equal what the batch gave them
+        in_batch = hashlib.sha256(spec2[:2].cpu().numpy().tobytes() + audio2[:2].cpu().numpy().tobytes()).hexdigest()[:16]
+    else:
+        in_batch = None
+    parity = {"bitwise": bool(int(counts[0]) == int(counts[1]) and len(set(digests)) == 1 and in_batch in (None, digest)),
+              "captures_recomputed_alone": int(counts[0]), "equal_to_batch_result": int(counts[1]),
+              "probe_digest_per_rank": digests, "probe_digest_in_rank0_batch": in_batch,
+              "what": "spectrum + WBFM audio of captures recomputed one at a time == their results inside the batch of "
+                      f"{B}; captures 0/1 of the job recomputed on every rank: sha256 equal on all GPUs (and across runs at other N)"}
+
+    # ---- configs[4] literally on ONE GPU: 4096 captures = 8 waves of 512, each wave's captures regenerated on the device
+    # (196.6 GB does not fit one B200); chains timed per wave with CUDA events, generation not timed ------------------
+    config4 = None
+    if world == 1 and args.config4_waves > 0:
+        ms_waves, t_wall = 0.0, time.perf_counter()
+        for w in range(args.config4_waves):
+            if w > 0:      # wave 0 is what is resident already (captures 0..B-1 of the job)
+                for c in range(B):
+                    kind = pkg.SYNTH_MULTITONE if (w * B + c) % 2 == 0 else pkg.SYNTH_WBFM
+                    sdr.synth_fill_dev(iq.data_ptr() + c * CAPTURE_BYTES, 1, CAPTURE_BYTES, kind, first_capture=w * B + c)
+                sdr.sync()
+            sdr.timer_start()
+            step(3)
+            ms_waves += sdr.timer_stop_ms()
+        n_cap4 = args.config4_waves * B
+        config4 = {"captures": n_cap4, "waves": args.config4_waves, "captures_per_wave": B, "ms_chains": ms_waves,
+                   "MSps": n_cap4 * CAPTURE_SAMPLES / (ms_waves * 1e-3) / 1e6,
+                   "wall_s_with_regeneration": time.perf_counter() - t_wall,
+                   "last_wave_checksum": float(spec2[B - 1].sum()),
+                   "note": "configs[4] on one GPU: waves share one 24.6 GB input buffer, regenerated between waves (not timed)"}
+
     # ---- N > 1 only, informative: the one exchange step the path can have -- ONE 10 s capture split in time
     # across the ranks, bin sums combined by the fused finalize + NVLink peer-memory all-reduce kernel
     # (csrc/exchange.cuh).  Not part of `value`; a failure here is reported, never fatal. --------------------
@@ -399,9 +520,32 @@ def main():
     for _ in range(e2e_steps):
         sdr.batch_host(pkg.CHAIN_SPECTRUM | pkg.CHAIN_WBFM, h_iq, E, CAPTURE_BYTES, spectrum=h_spec, wbfm=h_fm)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_mine = time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_mine)
     e2e_value = E * CAPTURE_SAMPLES * world * e2e_steps / e2e_s / 1e6
     checksum = float(h_spec[:1024].sum()) + float(h_fm[:1000].sum())
+
+    # what the host can feed: every rank at once does a PLAIN pinned cudaMemcpyAsync H2D of the same bytes from the same
+    # buffer (no kernels, no D2H) -- the ceiling b200sdr_batch_host is judged against (PCIe switch / root-complex topology
+    # and host memory are shared by the ranks, so the aggregate is not N x the single-GPU figure)
+    dst = torch.empty(E * CAPTURE_BYTES, dtype=torch.uint8, device="cuda")
+    src_t = torch.from_numpy(h_iq)          # the library's pinned buffer: cudaMemcpyAsync treats it as pinned
+    for _ in range(2):
+        dst.copy_(src_t, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dst.copy_(src_t, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_mine = time.perf_counter() - t0
+    h2d_s = max_over_ranks(h2d_mine)
+    del dst
+    per_rank = [(E * CAPTURE_BYTES * e2e_steps / e2e_mine / 1e9, E * CAPTURE_BYTES * e2e_steps / h2d_mine / 1e9)]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, (E * CAPTURE_BYTES * e2e_steps / e2e_mine / 1e9, E * CAPTURE_BYTES * e2e_steps / h2d_mine / 1e9))
+    h2d_agg = E * CAPTURE_BYTES * world * e2e_steps / h2d_s / 1e9
+    e2e_agg = E * CAPTURE_BYTES * world * e2e_steps / e2e_s / 1e9
     for p in (hp, sp, fp):
         sdr.pinned_free(p)
 
@@ -446,26 +590,30 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(os.cpu_count() or 1, 12.0)
+        arm = CpuArm()
+        cpu = arm.baseline(os.cpu_count() or 1, 12.0)
+        cpu["config0"] = arm.config0(os.cpu_count() or 1)
 
+    traffic_ratio, traffic_src = load_traffic_ratio()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[4] per-GPU share (= configs[1] spectrum + configs[2] WBFM on every capture): "
-                                   f"{B} x 10 s captures (48 MB u8 I/Q each) per GPU, both chains per step",
-                       "captures_per_gpu": B, "capture_seconds": 10, "sample_rate": 2.4e6, "nfft": 1024, "hop": 512,
-                       "window": "hann", "cache": f"inputs {B * CAPTURE_BYTES / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
-                       "parallelism": f"captures sharded over {world} GPU(s), no collective"},
+            "config": workload_config(B, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": E * CAPTURE_BYTES,
                     "d2h_bytes_per_step": E * (1024 + n_audio) * 4, "captures_per_step": E, "steps": e2e_steps,
-                    "api": "b200sdr_batch_host (pinned host -> H2D -> kernels -> D2H)", "checksum": checksum},
+                    "api": "b200sdr_batch_host (pinned host -> H2D -> kernels -> D2H)", "checksum": checksum,
+                    "h2d_GBps_aggregate": e2e_agg, "h2d_GBps_per_rank": [round(a, 2) for a, _ in per_rank],
+                    "h2d_ceiling": {"what": "all ranks at once: plain pinned cudaMemcpyAsync H2D of the same bytes, no kernels",
+                                    "GBps_aggregate": h2d_agg, "GBps_per_rank": [round(b, 2) for _, b in per_rank]},
+                    "frac_of_h2d_ceiling": e2e_agg / h2d_agg},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_spectrum (+k_spectrum_finalize)", "achieved": spec_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": spec_gbs / hbm_peak,
-                         "traffic": 1.0119 * 2.0 * B * CAPTURE_SAMPLES,  # bytes per launch: ncu dram read+write = 1.0119 x algorithmic (profiles/r1_ncu_summary.txt: 1.5424 GB read + 11.9 MB written for 1.536 GB of input)
+                         "traffic": (traffic_ratio * 2.0 * B * CAPTURE_SAMPLES) if traffic_ratio else None,  # bytes per launch
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": 2.0,
                          "note": "FP32-pipe bound, not HBM bound (DESIGN.md 5.1): 1028 FP32-pipe cycles per 1024-pt frame per SM "
@@ -492,8 +640,11 @@ def main():
                        "note": "config[3], secondary; not part of `value`"},
             },
             "ingest": ingest,
+            "parity": parity,
             "cpu_baseline": cpu,
         }
+        if config4 is not None:
+            line["config4_single_gpu"] = config4
         if split is not None:
             line["split_capture"] = split
         print(json.dumps(line))

@@ -92,7 +92,9 @@ typedef struct b200sdr_config {
     uint32_t slot_bytes;    /* bytes per slot = largest `len` process_samples accepts.
                                Reference live value 512 (usbh_rtlsdr.c:230); BASELINE block
                                262144 = DEFAULT_BUF_LENGTH (usbh_rtlsdr.h:277-278).            */
-    uint32_t audio_capacity;/* streaming audio FIFO capacity in float samples per chain       */
+    uint32_t audio_capacity;/* streaming audio FIFO capacity in float samples per chain; raised by
+                               b200sdr_create to what ONE full slot produces (slot_bytes/100 + 16 with
+                               WBFM, slot_bytes/600 + 16 with AM) so a block always fits an empty FIFO */
     uint32_t submit_bytes;  /* process_samples() appends blocks to the open pinned slot and
                                submits it (one H2D + one pass of the chains) once this many
                                bytes are pending or the next block would not fit; 0 = slot_bytes.
@@ -187,7 +189,10 @@ B200SDR_API int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const 
  * passed in rank order to exchange_connect.  Contexts living in one process use
  * exchange_connect_local instead.  All ranks must make the same sequence of split calls.
  * split_spectrum_dev is asynchronous on the ctx compute stream; exchange_wait blocks and
- * returns B200SDR_FAIL if a peer did not arrive within ~5 s (the kernel's wait is bounded).
+ * returns B200SDR_FAIL if a peer did not arrive within ~5 s (the kernel's wait is bounded); the
+ * output spectrum is then NaN-filled, and because the ranks no longer agree on the call number the
+ * exchange must be destroyed and re-created (exchange_destroy / _create / _connect) on EVERY rank
+ * before the next split call.
  * Demodulators are not split this way (carried IIR state): they stay one capture per GPU.
  * ------------------------------------------------------------------------------------------ */
 B200SDR_API int32_t b200sdr_exchange_create(b200sdr_ctx *ctx, uint32_t world, uint32_t rank, uint8_t *ipc_handle_out64);

@@ -71,8 +71,8 @@ typedef struct b200sdr_ctl_xfer {
  * transfer what the reference firmware emits (108 transfers; tests/test_frontend_parity.py records the
  * reference's own FSM in oracle A).
  * Writes min(capacity, n) entries, *n_out = n.  B200SDR_OK; B200SDR_NOT_SUPPORTED for a rate the resampler cannot
- * produce or a FIR coefficient out of range (the list is still produced, like the firmware would);
- * B200SDR_BUSY if capacity < n; B200SDR_FAIL for null pointers / zero rate. */
+ * produce or a FIR coefficient out of range (nothing is written and *n_out = 0: no list with undefined register
+ * values ever leaves this function); B200SDR_BUSY if capacity < n; B200SDR_FAIL for null pointers / zero rate. */
 B200SDR_API int32_t b200sdr_rtl_init_sequence(uint32_t samp_rate, uint32_t xtal_hz, const int32_t *fir16, uint32_t flags,
                                               b200sdr_ctl_xfer *out, uint32_t capacity, uint32_t *n_out);
 

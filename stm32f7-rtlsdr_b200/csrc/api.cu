@@ -30,6 +30,19 @@ namespace {
 constexpr uint64_t kStreamSlack = 16384;     /* device stream buffer = ring_slots x slot_bytes + this; the unread
                                                 tail carried over a wrap is < 2048 + 400 bytes           */
 constexpr uint64_t kWaveBytesDefault = 192ull << 20;
+/* measurement knobs (tools/e2e_multi_probe.py), not part of the ABI: B200SDR_WAVE_MB overrides the wave size of
+ * b200sdr_batch_host, B200SDR_PINNED_WC=1 makes b200sdr_host_alloc_pinned write-combined */
+uint64_t wave_bytes_target()
+{
+    const char *e = getenv("B200SDR_WAVE_MB");
+    const long mb = e ? atol(e) : 0;
+    return mb > 0 ? (uint64_t)mb << 20 : kWaveBytesDefault;
+}
+unsigned pinned_flags()
+{
+    const char *e = getenv("B200SDR_PINNED_WC");
+    return (e && e[0] == '1') ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
+}
 
 struct AudioFifo {
     float *d_buf = nullptr;   /* device FIFO storage: valid floats are d_buf[head .. head + count)  */
@@ -43,7 +56,8 @@ struct AudioFifo {
 struct b200sdr_ctx {
     b200sdr_config cfg{};
     int device = 0, sm_count = 148;
-    cudaStream_t s_copy = nullptr, s_compute = nullptr;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    bool failed = false;     /* sticky: a chain failed after its H2D was enqueued (see commit_slot) */
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     uint64_t launches = 0;
     char err[256] = {0};
@@ -66,7 +80,7 @@ struct b200sdr_ctx {
     float *d_res_spec = nullptr, *d_res_fm = nullptr, *d_res_am = nullptr; /* batch_host result staging */
     size_t res_spec_floats = 0, res_fm_floats = 0, res_am_floats = 0;
     uint8_t *d_wave[2] = {nullptr, nullptr}; size_t wave_bytes = 0;
-    cudaEvent_t ev_wave_copied[2] = {nullptr, nullptr}, ev_wave_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_wave_copied[2] = {nullptr, nullptr}, ev_wave_done[2] = {nullptr, nullptr}, ev_wave_out[2] = {nullptr, nullptr};
 
     /* ingest ring */
     uint8_t *h_ring = nullptr;          /* pinned: ring_slots x slot_bytes                          */
@@ -99,6 +113,7 @@ struct b200sdr_ctx {
     int amf_state_cur = 0;
     AmBackState *d_amb_state = nullptr; AudioFifo am_fifo;
     float *d_am_env_stream = nullptr;
+    uint32_t am_env_cap = 0;
 
     /* split-capture exchange (K6): own mailbox, the peers' mailboxes as mapped here, call counter */
     float *d_mailbox = nullptr;
@@ -148,7 +163,8 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
 {
     b200::SpectrumPlan pl = b200::plan_spectrum(len_bytes, n_captures, (uint32_t)ctx->sm_count);
     if (pl.frames == 0) return B200SDR_OK;
-    int rc = ensure_floats(ctx, &ctx->d_partials, &ctx->partials_floats, (size_t)n_captures * pl.ctas_per_capture * 1024);
+    if (pl.total_units > 0xffffffffull) return fail(ctx, B200SDR_NOT_SUPPORTED, "batch too large (32-bit work-unit index)");
+    int rc = ensure_floats(ctx, &ctx->d_partials, &ctx->partials_floats, (size_t)pl.total_units * 1024);
     if (rc) return rc;
     SpectrumParams p{};
     p.iq = iq_dev;
@@ -158,10 +174,11 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     p.window = ctx->d_window[ctx->cfg.window];
     p.twiddle = ctx->d_twiddle;
     p.partials = ctx->d_partials;
-    p.ctas_per_capture = pl.ctas_per_capture;
+    p.units_per_capture = pl.units_per_capture;
+    p.total_units = (uint32_t)pl.total_units;
     p.ema_beta = ctx->cfg.ema_beta;
     p.ema_log2_decay = log2f(1.0f - ctx->cfg.ema_beta);
-    dim3 grid(pl.ctas_per_capture, n_captures);
+    dim3 grid(pl.grid);
     if (ema) k_spectrum<true><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
     else k_spectrum<false><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
     CU(cudaGetLastError());
@@ -169,7 +186,7 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     if (!finalize) return B200SDR_OK; /* the caller reduces ctx->d_partials itself (split-capture exchange) */
     float scale = ema ? 1.0f : 1.0f / (float)pl.frames;
     if (use_scale_override) scale = scale_override;
-    k_spectrum_finalize<<<dim3(4, n_captures), 256, 0, ctx->s_compute>>>(ctx->d_partials, pl.ctas_per_capture, scale,
+    k_spectrum_finalize<<<dim3(4, n_captures), 256, 0, ctx->s_compute>>>(ctx->d_partials, pl.units_per_capture, scale,
                                                                          carry, carry_scale, out_dev);
     CU(cudaGetLastError());
     ctx->launches += 1;
@@ -285,6 +302,7 @@ int stream_am(b200sdr_ctx *ctx)
 {
     const uint32_t n_chunks = (uint32_t)((ctx->wpos - ctx->am_off) / (2 * B200_AM_CHUNK));
     if (n_chunks == 0) return B200SDR_OK;
+    if (n_chunks > ctx->am_env_cap) return fail(ctx, B200SDR_FAIL, "AM envelope workspace too small for the pending stream");
     const uint64_t a0 = (2 * ctx->am_chunks + 2) / 3, a1 = (2 * (ctx->am_chunks + n_chunks) + 2) / 3;
     const uint32_t n_audio = (uint32_t)(a1 - a0);
     float *am_out = nullptr;
@@ -363,14 +381,18 @@ int reset_stream_state(b200sdr_ctx *ctx)
 
 const float *synth_lut_host()
 {
-    static float lut[B200SDR_SYNTH_LUT_SIZE + 1];
-    static bool ready = false;
-    if (!ready) {
-        for (unsigned i = 0; i <= B200SDR_SYNTH_LUT_SIZE; ++i)
-            lut[i] = (float)sin(2.0 * b200::kPi * (double)(i % B200SDR_SYNTH_LUT_SIZE) / (double)B200SDR_SYNTH_LUT_SIZE);
-        ready = true;
-    }
-    return lut;
+    /* filled by the constructor of a function-local static: C++11 makes that initialisation thread-safe, so
+     * contexts created from several threads at once never see a partly filled table */
+    struct Lut {
+        float v[B200SDR_SYNTH_LUT_SIZE + 1];
+        Lut()
+        {
+            for (unsigned i = 0; i <= B200SDR_SYNTH_LUT_SIZE; ++i)
+                v[i] = (float)sin(2.0 * b200::kPi * (double)(i % B200SDR_SYNTH_LUT_SIZE) / (double)B200SDR_SYNTH_LUT_SIZE);
+        }
+    };
+    static const Lut lut;
+    return lut.v;
 }
 
 /* end of the stream buffer: move the unread tail (what the slowest enabled chain has not consumed:
@@ -404,27 +426,37 @@ int commit_slot(b200sdr_ctx *ctx, uint32_t slot, uint32_t len)
         if (wrc) return wrc;
     }
     CU(cudaMemcpyAsync(ctx->d_stream + ctx->wpos, h_slot, len, cudaMemcpyHostToDevice, ctx->s_copy));
-    CU(cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy));
-    CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[slot], 0));
+    /* from here on the pinned slot has a copy in flight: it is marked used and the ring moves on whatever
+     * happens below, so the slot is never handed out again before ev_copied says so */
+    ctx->slot_used[slot] = 1;
+    ctx->ring_head = (slot + 1) % ctx->cfg.ring_slots;
+    ctx->submits += 1;
     ctx->last_pos = ctx->wpos;
     ctx->wpos += len;
     int rc = B200SDR_OK;
-    if (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM) { rc = stream_spectrum(ctx); if (rc) return rc; }
-    if (ctx->cfg.chains & B200SDR_CHAIN_WBFM) { rc = stream_wbfm(ctx); if (rc) return rc; }
-    if (ctx->cfg.chains & B200SDR_CHAIN_AM) { rc = stream_am(ctx); if (rc) return rc; }
-    if (ctx->cfg.chains & B200SDR_CHAIN_COUNTER) { rc = stream_counter(ctx, len); if (rc) return rc; }
-    ctx->slot_used[slot] = 1;
-    ctx->submits += 1;
-    ctx->ring_head = (slot + 1) % ctx->cfg.ring_slots;
-    return B200SDR_OK;
+    cudaError_t e = cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[slot], 0);
+    if (e != cudaSuccess) rc = fail(ctx, B200SDR_FAIL, "ring slot hand-over", e);
+    if (!rc && (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM)) rc = stream_spectrum(ctx);
+    if (!rc && (ctx->cfg.chains & B200SDR_CHAIN_WBFM)) rc = stream_wbfm(ctx);
+    if (!rc && (ctx->cfg.chains & B200SDR_CHAIN_AM)) rc = stream_am(ctx);
+    if (!rc && (ctx->cfg.chains & B200SDR_CHAIN_COUNTER)) rc = stream_counter(ctx, len);
+    if (rc) {
+        /* a chain did not run over bytes that are already part of the stream: the chains' read offsets no
+         * longer agree with `wpos`, so the stream is dead until b200sdr_reset() starts a new capture.
+         * Sticky: every later streaming call returns B200SDR_FAIL instead of computing on a torn stream. */
+        ctx->failed = true;
+    }
+    return rc;
 }
 
 /* submit whatever process_samples has appended to the open slot (no-op when nothing is pending) */
 int flush_pending(b200sdr_ctx *ctx)
 {
     if (ctx->pending == 0) return B200SDR_OK;
+    if (ctx->failed) return fail(ctx, B200SDR_FAIL, "stream failed earlier: call b200sdr_reset");
     const uint32_t n = ctx->pending;
-    ctx->pending = 0;
+    ctx->pending = 0; /* on failure commit_slot latches ctx->failed: the bytes are never silently dropped */
     return commit_slot(ctx, ctx->ring_head, n);
 }
 
@@ -514,6 +546,9 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     if (cfg.slot_bytes < 4 || (cfg.slot_bytes & 3u)) return B200SDR_NOT_SUPPORTED; /* multiple-of-4 rule */
     if (cfg.avg_mode == B200SDR_AVG_EMA && !(cfg.ema_beta > 0.0f && cfg.ema_beta < 1.0f)) return B200SDR_NOT_SUPPORTED;
     if (cfg.audio_capacity < 4096) cfg.audio_capacity = 4096;
+    /* one full slot must fit an EMPTY FIFO, or process_samples would answer BUSY for ever (fifo_room) */
+    if ((cfg.chains & B200SDR_CHAIN_WBFM) && cfg.audio_capacity < cfg.slot_bytes / 100 + 16) cfg.audio_capacity = cfg.slot_bytes / 100 + 16;
+    if ((cfg.chains & B200SDR_CHAIN_AM) && cfg.audio_capacity < cfg.slot_bytes / 600 + 16) cfg.audio_capacity = cfg.slot_bytes / 600 + 16;
     if (cfg.submit_bytes > cfg.slot_bytes) return B200SDR_NOT_SUPPORTED;
 
     int n_dev = 0;
@@ -545,11 +580,13 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ctx->ev_t0));
     CK(cudaEventCreate(&ctx->ev_t1));
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&ctx->ev_wave_copied[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_wave_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_wave_out[i], cudaEventDisableTiming));
     }
     CK(cudaFuncSetAttribute(k_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_SPEC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_SPEC_SMEM_BYTES));
@@ -605,7 +642,9 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     CK(cudaMalloc((void **)&ctx->d_fm_state, 2 * sizeof(FmState)));
     CK(cudaMalloc((void **)&ctx->d_amf_state, 2 * sizeof(AmFrontState)));
     CK(cudaMalloc((void **)&ctx->d_amb_state, sizeof(AmBackState)));
-    CK(cudaMalloc((void **)&ctx->d_am_env_stream, ((size_t)cfg.slot_bytes / 400 + 8) * sizeof(float)));
+    /* one envelope sample per 400-byte chunk of whatever a launch can see: sized from the whole stream buffer */
+    ctx->am_env_cap = (uint32_t)(ctx->stream_cap / (2 * B200_AM_CHUNK) + 8);
+    CK(cudaMalloc((void **)&ctx->d_am_env_stream, (size_t)ctx->am_env_cap * sizeof(float)));
     ctx->fm_fifo.capacity = cfg.audio_capacity;
     ctx->am_fifo.capacity = cfg.audio_capacity;
     CK(cudaMalloc((void **)&ctx->fm_fifo.d_buf, (size_t)cfg.audio_capacity * sizeof(float)));
@@ -635,6 +674,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_wave_copied[i]) cudaEventDestroy(ctx->ev_wave_copied[i]);
         if (ctx->ev_wave_done[i]) cudaEventDestroy(ctx->ev_wave_done[i]);
+        if (ctx->ev_wave_out[i]) cudaEventDestroy(ctx->ev_wave_out[i]);
         if (ctx->d_wave[i]) cudaFree(ctx->d_wave[i]);
     }
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -648,6 +688,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     for (void *p : dev_ptrs) if (p) cudaFree(p);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     delete ctx;
     return B200SDR_OK;
 }
@@ -660,6 +701,7 @@ int32_t process_samples(const uint8_t *iq, uint32_t len, void *vctx)
     if (len == 0) return B200SDR_OK;
     if ((len & 3u) || len > ctx->cfg.slot_bytes) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4 and <= slot_bytes");
     if (ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "a ring slot is acquired; commit it first");
+    if (ctx->failed) return fail(ctx, B200SDR_FAIL, "stream failed earlier: call b200sdr_reset");
     DeviceGuard guard(ctx->device);
     /* blocks are appended to the open pinned slot; the slot is submitted (one H2D + one pass of the
      * chains) once cfg.submit_bytes are pending or the next block would not fit */
@@ -687,6 +729,7 @@ int32_t b200sdr_ring_acquire(b200sdr_ctx *ctx, uint8_t **slot_ptr, uint32_t *slo
 {
     if (!ctx || !slot_ptr) return B200SDR_FAIL;
     if (ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "slot already acquired");
+    if (ctx->failed) return fail(ctx, B200SDR_FAIL, "stream failed earlier: call b200sdr_reset");
     DeviceGuard guard(ctx->device);
     int rc = flush_pending(ctx); /* keep stream order: blocks appended by process_samples go first */
     if (rc) return rc;
@@ -704,6 +747,7 @@ int32_t b200sdr_ring_commit(b200sdr_ctx *ctx, uint32_t len)
     if (!ctx) return B200SDR_FAIL;
     if (!ctx->slot_acquired) return fail(ctx, B200SDR_FAIL, "no slot acquired");
     if ((len & 3u) || len > ctx->cfg.slot_bytes) return fail(ctx, B200SDR_NOT_SUPPORTED, "len must be a multiple of 4 and <= slot_bytes");
+    if (ctx->failed) { ctx->slot_acquired = false; return fail(ctx, B200SDR_FAIL, "stream failed earlier: call b200sdr_reset"); }
     if (!fifo_room(ctx, len)) { ctx->busy_returns++; return fail(ctx, B200SDR_BUSY, "audio FIFO full: call b200sdr_get_audio"); }
     ctx->slot_acquired = false;
     if (len == 0) return B200SDR_OK;
@@ -733,6 +777,8 @@ int32_t b200sdr_reset(b200sdr_ctx *ctx)
     if (!ctx) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
     ctx->pending = 0; /* blocks not yet submitted belong to the capture being forgotten */
+    ctx->failed = false;
+    ctx->slot_acquired = false;
     int rc = b200sdr_sync(ctx);
     if (rc) return rc;
     return reset_stream_state(ctx);
@@ -850,7 +896,7 @@ int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const uint8_t *iq_
     if ((chains & B200SDR_CHAIN_WBFM) && !wbfm_audio_host) return B200SDR_FAIL;
     if ((chains & B200SDR_CHAIN_AM) && !am_audio_host) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
-    uint64_t per_wave = kWaveBytesDefault / len_each;
+    uint64_t per_wave = wave_bytes_target() / len_each;
     if (per_wave < 1) per_wave = 1;
     if (per_wave > n_captures) per_wave = n_captures;
     const size_t wave_bytes = (size_t)per_wave * len_each;
@@ -870,41 +916,44 @@ int32_t b200sdr_batch_host(b200sdr_ctx *ctx, uint32_t chains, const uint8_t *iq_
     if (chains & B200SDR_CHAIN_SPECTRUM) { rca = ensure_floats(ctx, &ctx->d_res_spec, &ctx->res_spec_floats, 2 * per_wave * 1024); if (rca) return rca; d_spec = ctx->d_res_spec; }
     if (chains & B200SDR_CHAIN_WBFM) { rca = ensure_floats(ctx, &ctx->d_res_fm, &ctx->res_fm_floats, 2 * per_wave * fm_len); if (rca) return rca; d_fm = ctx->d_res_fm; }
     if (chains & B200SDR_CHAIN_AM) { rca = ensure_floats(ctx, &ctx->d_res_am, &ctx->res_am_floats, 2 * per_wave * am_len); if (rca) return rca; d_am = ctx->d_res_am; }
+    /* three streams: H2D of wave w+1 (copy), kernels of wave w (compute), D2H of the results of wave w-1 (d2h) --
+     * PCIe is full duplex, and the kernels of the next wave do not wait for a read-back */
     int rc = B200SDR_OK;
     bool used[2] = {false, false};
     uint32_t wave = 0;
     for (uint64_t c0 = 0; c0 < n_captures && rc == B200SDR_OK; c0 += per_wave, ++wave) {
         const int b = (int)(wave & 1);
         const uint32_t nc = (uint32_t)((n_captures - c0 < per_wave) ? n_captures - c0 : per_wave);
-        if (used[b]) CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_wave_done[b], 0));
+        if (used[b]) {
+            CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_wave_done[b], 0));   /* wave buffer: kernels of wave w-2 done */
+            CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_wave_out[b], 0)); /* result buffers: read-back of wave w-2 done */
+        }
         CU(cudaMemcpyAsync(ctx->d_wave[b], iq_host + c0 * len_each, (size_t)nc * len_each, cudaMemcpyHostToDevice, ctx->s_copy));
         CU(cudaEventRecord(ctx->ev_wave_copied[b], ctx->s_copy));
         CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_wave_copied[b], 0));
-        if (chains & B200SDR_CHAIN_SPECTRUM) {
-            float *o = d_spec + (size_t)b * per_wave * 1024;
-            rc = b200sdr_batch_spectrum_dev(ctx, ctx->d_wave[b], nc, len_each, o);
-            if (rc) break;
-            CU(cudaMemcpyAsync(spectrum_host + c0 * 1024, o, (size_t)nc * 1024 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
-        }
-        if (chains & B200SDR_CHAIN_WBFM) {
-            float *o = d_fm + (size_t)b * per_wave * fm_len;
-            rc = launch_wbfm_batch(ctx, ctx->d_wave[b], nc, len_each, o, nullptr);
-            if (rc) break;
-            CU(cudaMemcpyAsync(wbfm_audio_host + c0 * fm_len, o, (size_t)nc * fm_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
-        }
-        if (chains & B200SDR_CHAIN_AM) {
-            float *o = d_am + (size_t)b * per_wave * am_len;
-            rc = launch_am_batch(ctx, ctx->d_wave[b], nc, len_each, o);
-            if (rc) break;
-            CU(cudaMemcpyAsync(am_audio_host + c0 * am_len, o, (size_t)nc * am_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
-        }
+        float *o_spec = d_spec ? d_spec + (size_t)b * per_wave * 1024 : nullptr;
+        float *o_fm = d_fm ? d_fm + (size_t)b * per_wave * fm_len : nullptr;
+        float *o_am = d_am ? d_am + (size_t)b * per_wave * am_len : nullptr;
+        if (chains & B200SDR_CHAIN_SPECTRUM) { rc = b200sdr_batch_spectrum_dev(ctx, ctx->d_wave[b], nc, len_each, o_spec); if (rc) break; }
+        if (chains & B200SDR_CHAIN_WBFM) { rc = launch_wbfm_batch(ctx, ctx->d_wave[b], nc, len_each, o_fm, nullptr); if (rc) break; }
+        if (chains & B200SDR_CHAIN_AM) { rc = launch_am_batch(ctx, ctx->d_wave[b], nc, len_each, o_am); if (rc) break; }
         CU(cudaEventRecord(ctx->ev_wave_done[b], ctx->s_compute));
+        CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_wave_done[b], 0));
+        if (chains & B200SDR_CHAIN_SPECTRUM)
+            CU(cudaMemcpyAsync(spectrum_host + c0 * 1024, o_spec, (size_t)nc * 1024 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (chains & B200SDR_CHAIN_WBFM)
+            CU(cudaMemcpyAsync(wbfm_audio_host + c0 * fm_len, o_fm, (size_t)nc * fm_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (chains & B200SDR_CHAIN_AM)
+            CU(cudaMemcpyAsync(am_audio_host + c0 * am_len, o_am, (size_t)nc * am_len * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CU(cudaEventRecord(ctx->ev_wave_out[b], ctx->s_d2h));
         used[b] = true;
     }
-    cudaError_t e1 = cudaStreamSynchronize(ctx->s_copy), e2 = cudaStreamSynchronize(ctx->s_compute);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_copy), e2 = cudaStreamSynchronize(ctx->s_compute),
+                e3 = cudaStreamSynchronize(ctx->s_d2h);
     if (rc) return rc;
     if (e1 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "copy stream", e1);
     if (e2 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "compute stream", e2);
+    if (e3 != cudaSuccess) return fail(ctx, B200SDR_FAIL, "read-back stream", e3);
     return B200SDR_OK;
 }
 
@@ -1266,7 +1315,7 @@ int32_t b200sdr_split_spectrum_dev(b200sdr_ctx *ctx, const uint8_t *iq_slice_dev
     if (rc) return rc;
     ExchangeParams p{};
     p.partials = ctx->d_partials;
-    p.ctas_per_capture = pl.frames ? pl.ctas_per_capture : 0; /* a rank without frames contributes zeros */
+    p.ctas_per_capture = pl.frames ? pl.units_per_capture : 0; /* a rank without frames contributes zeros */
     p.scale = 1.0f / (float)frames_total;
     p.out = spectrum_dev;
     for (uint32_t r = 0; r < ctx->xchg_world; ++r) p.mail[r] = ctx->peer_mail[r];
@@ -1333,7 +1382,7 @@ int32_t b200sdr_host_alloc_pinned(b200sdr_ctx *ctx, uint64_t bytes, void **out_h
 {
     if (!ctx || !out_host) return B200SDR_FAIL;
     DeviceGuard guard(ctx->device);
-    CU(cudaHostAlloc(out_host, bytes ? bytes : 16, cudaHostAllocDefault));
+    CU(cudaHostAlloc(out_host, bytes ? bytes : 16, pinned_flags()));
     return B200SDR_OK;
 }
 int32_t b200sdr_host_free_pinned(b200sdr_ctx *ctx, void *host)

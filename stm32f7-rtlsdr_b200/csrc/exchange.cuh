@@ -14,7 +14,9 @@
  * Mailbox (per rank, cudaMalloc'd, zeroed):   float slots[2][world][1024];  uint32 flags[2][world][4]
  * indexed by the parity of the call's sequence number: a rank can only reach call k+2 after it saw
  * every peer's flag of call k+1, i.e. after every peer finished reading the slots of call k.
- * The wait is bounded (clock64): a missing peer makes the call fail, it cannot hang the GPU.
+ * The wait is bounded (clock64): a missing peer makes the call fail, it cannot hang the GPU; the output is
+ * then NaN-filled.  After a failed call the ranks no longer agree on the sequence number / slot parity:
+ * the exchange has to be destroyed and re-created on EVERY rank (b200sdr_exchange_destroy / _create / _connect).
  */
 #ifndef B200_EXCHANGE_CUH
 #define B200_EXCHANGE_CUH
@@ -86,7 +88,8 @@ __global__ void __launch_bounds__(256) k_spectrum_finalize_exchange(ExchangePara
         }
     }
     __syncthreads();
-    if (s_timeout) {
+    if (s_timeout) { /* a peer never arrived: no stale spectrum is left behind, and the host sees the status word */
+        p.out[k] = __int_as_float(0x7fc00000);
         if (threadIdx.x == 0) *p.status = 1u;
         return;
     }

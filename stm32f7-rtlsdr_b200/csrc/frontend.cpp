@@ -13,15 +13,21 @@ extern "C" {
 int32_t b200sdr_rtl_resampler(uint32_t samp_rate, uint32_t xtal_hz, b200sdr_rtl_rate *out)
 {
     if (!out || samp_rate == 0) return B200SDR_FAIL;
+    /* the rate check comes FIRST (the reference checks a compile-time constant, :677-681): below 28 126 S/s at
+     * 28.8 MHz the quotient does not fit 32 bits and the conversion would be undefined; *out stays zeroed */
+    out->rsamp_ratio = out->real_rsamp_ratio = 0;
+    out->real_rate = 0.0;
+    if (samp_rate <= 225000u || samp_rate > 3200000u || (samp_rate > 300000u && samp_rate <= 900000u)) return B200SDR_NOT_SUPPORTED;
     const double scaled_xtal = (double)xtal_hz * 4194304.0;
-    uint32_t ratio = (uint32_t)(scaled_xtal / (double)samp_rate);
+    const double quotient = scaled_xtal / (double)samp_rate;
+    if (!(quotient < 4294967296.0)) return B200SDR_NOT_SUPPORTED; /* absurd crystal: same guard */
+    uint32_t ratio = (uint32_t)quotient;
     ratio &= 0x0FFFFFFCu;
     const uint32_t applied = ratio | ((ratio & 0x08000000u) << 1);
     out->rsamp_ratio = ratio;
     out->real_rsamp_ratio = applied;
     out->real_rate = scaled_xtal / (double)applied;
-    const bool unsupported = samp_rate <= 225000u || samp_rate > 3200000u || (samp_rate > 300000u && samp_rate <= 900000u);
-    return unsupported ? B200SDR_NOT_SUPPORTED : B200SDR_OK;
+    return B200SDR_OK;
 }
 
 /* RTL/Inc/usbh_rtlsdr.h:340-345 (the DAB/FM coefficients of the vendor driver) */
@@ -105,6 +111,10 @@ int32_t b200sdr_rtl_init_sequence(uint32_t samp_rate, uint32_t xtal_hz, const in
     const int32_t fir_rc = b200sdr_rtl_fir_pack(coeff, fir);
     b200sdr_rtl_rate rate{};
     const int32_t rate_rc = b200sdr_rtl_resampler(samp_rate, xtal_hz, &rate);
+    if (fir_rc != B200SDR_OK || rate_rc != B200SDR_OK) { /* nothing is emitted for parameters the chip cannot take */
+        *n_out = 0;
+        return B200SDR_NOT_SUPPORTED;
+    }
 
     SeqWriter w{out, capacity, 0, 0};
     w.step = 0;  w.write_reg(USBB, USB_SYSCTL, 0x09, 1);            /* dummy write */
@@ -144,8 +154,7 @@ int32_t b200sdr_rtl_init_sequence(uint32_t samp_rate, uint32_t xtal_hz, const in
     w.step = 32; w.write_reg(USBB, USB_EPA_CTL, 0x1002, 2);         /* reset the bulk FIFO (mandatory) */
     w.step = 33; w.write_reg(USBB, USB_EPA_CTL, 0x0000, 2);
     *n_out = w.n;
-    if (w.n > capacity) return B200SDR_BUSY;
-    return (fir_rc != B200SDR_OK || rate_rc != B200SDR_OK) ? B200SDR_NOT_SUPPORTED : B200SDR_OK;
+    return w.n > capacity ? B200SDR_BUSY : B200SDR_OK;
 }
 
 /* E4K_compute_pll_params, RTL/Src/tuner_e4k.c:689-737 with its band table :301-312 and

@@ -27,29 +27,38 @@ inline uint64_t wbfm_audio_len(uint64_t len_bytes) { return ceil_div(wbfm_disc_l
 inline uint64_t am_y2_len(uint64_t len_bytes) { return ceil_div(ceil_div(len_bytes / 2, 20), 10); }
 inline uint64_t am_audio_len(uint64_t len_bytes) { return ceil_div(2 * am_y2_len(len_bytes), 3); }
 
-/* ---- spectrum: frames per warp so that the grid has a few waves of CTAs ---- */
+/* ---- spectrum: work units of 4 x frames_per_warp consecutive frames, persistent grid ----
+ * frames_per_warp follows from the capture LENGTH only -- never from the batch size or the device -- so the
+ * summation tree of one capture (frames in a warp, warps in a unit, units in k_spectrum_finalize) and with it
+ * every bit of its spectrum is the same for the capture alone, in a batch of 512 and in a 4096 / N shard on
+ * any GPU (bitwise per-capture results on 1 vs 8 GPUs).  The length rule: as many
+ * units as one capture needs to fill every resident CTA slot of a B200 once (2 x 148 slots x 4 warps),
+ * at most 64 frames per warp (the partial sums then stay below 2 % of the input bytes); a batch amortises
+ * the per-CTA prologue through the persistent grid instead of through longer warps. */
+constexpr uint32_t kSpecWarpsToFill = 2u * 148u * B200_SPEC_WARPS; /* a constant, not the device's SM count */
+constexpr uint32_t kSpecMaxFramesPerWarp = 64;
 struct SpectrumPlan {
-    uint32_t frames, frames_per_warp, ctas_per_capture;
+    uint32_t frames, frames_per_warp, units_per_capture, grid;
+    uint64_t total_units;
 };
+inline uint32_t spectrum_frames_per_warp(uint64_t frames)
+{
+    uint64_t fpw = ceil_div(frames, kSpecWarpsToFill);
+    if (fpw < 1) fpw = 1;
+    if (fpw > kSpecMaxFramesPerWarp) fpw = kSpecMaxFramesPerWarp;
+    return (uint32_t)fpw;
+}
 inline SpectrumPlan plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count)
 {
     SpectrumPlan pl{};
     pl.frames = (uint32_t)spectrum_frames(len_bytes);
     if (pl.frames == 0) return pl;
-    /* frames per warp (1..256) from a two-term cost model: a CTA costs a fixed prologue/epilogue
-     * (constants to registers, partial-sum reduction) plus fpw frames; two CTAs are resident per SM, so
-     * the batch runs in ceil(CTAs / (2 SMs)) waves.  Few frames per warp waste time in prologues (a single
-     * 10 s capture at fpw = 2 took 247 us), too many leave SMs idle in the last wave.  Units: 0.1 us. */
+    pl.frames_per_warp = spectrum_frames_per_warp(pl.frames);
+    pl.units_per_capture = (uint32_t)ceil_div(pl.frames, (uint64_t)pl.frames_per_warp * B200_SPEC_WARPS);
+    pl.total_units = (uint64_t)pl.units_per_capture * n_captures;
+    /* the device only decides how many CTAs share the units, which no result depends on */
     const uint64_t slots = (uint64_t)sm_count * B200_SPEC_MINB;
-    const uint64_t kCtaFixed = 30, kPerFrame = 13; /* ~3 us per CTA, ~1.3 us per frame with 2 warps per scheduler */
-    uint64_t best_cost = ~0ull, fpw = 1;
-    for (uint64_t f = 1; f <= 256; ++f) {
-        const uint64_t ctas = ceil_div(pl.frames, f * B200_SPEC_WARPS) * n_captures;
-        const uint64_t cost = ceil_div(ctas, slots) * (kCtaFixed + f * kPerFrame);
-        if (cost <= best_cost) { best_cost = cost; fpw = f; } /* ties: more frames per warp = fewer partials */
-    }
-    pl.frames_per_warp = (uint32_t)fpw;
-    pl.ctas_per_capture = (uint32_t)ceil_div(pl.frames, fpw * B200_SPEC_WARPS);
+    pl.grid = (uint32_t)(pl.total_units < slots ? pl.total_units : slots);
     return pl;
 }
 

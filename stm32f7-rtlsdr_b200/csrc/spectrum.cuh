@@ -18,12 +18,15 @@
  * memory once per CTA and then held in registers (250 registers, 2 CTAs of 4 warps per SM): the only
  * shared-memory traffic per frame is the transpose (DESIGN.md 5.1 has the A/B measurements; the
  * compile-time knobs below are the A/B switches of those measurements, defaults = shipped).
- * A warp walks `frames_per_warp` consecutive frames (hop 512) and keeps the 32 x 32 bin sums in
- * registers; the warps of a CTA are then added in a fixed order and one 1024-float partial per
- * CTA goes to a workspace that k_spectrum_finalize (or the split-capture exchange kernel) sums in a
- * fixed order -> deterministic results, no float atomics: the same batch shape gives the same bits
- * on every run and every GPU (the frames-per-warp split, hence the summation order, follows the
- * batch shape, plan.h).
+ * Work unit = (capture, 4 x frames_per_warp consecutive frames).  A warp walks `frames_per_warp`
+ * consecutive frames (hop 512) and keeps the 32 x 32 bin sums in registers; the four warps of the unit are
+ * then added in a fixed order and one 1024-float partial per UNIT goes to a workspace that
+ * k_spectrum_finalize (or the split-capture exchange kernel) sums in a fixed order -> deterministic
+ * results, no float atomics.  frames_per_warp follows from the capture LENGTH only (plan.h), so the
+ * summation tree of a capture -- hence every bit of its spectrum -- is the same whether the capture is
+ * processed alone, in a batch of 512 or in a 4096 / N shard on another GPU.  The grid is persistent
+ * (one CTA per resident slot, CTA b takes units b, b + grid, ...): the per-CTA prologue (constants to
+ * registers) is paid once however short the units are.
  *
  * Input access: lane t reads the 2-byte sample n = t + 32 j straight from global memory
  * (a warp reads 64 contiguous bytes per j; both halves of every 128-byte line are used by
@@ -97,8 +100,9 @@ struct SpectrumParams {
     uint32_t frames_per_warp; /* consecutive frames walked by one warp                           */
     const float *window;      /* 1024 floats                                                     */
     const float2 *twiddle;    /* 1024 entries: e^{-2 pi i m / 1024}                              */
-    float *partials;          /* [capture][ctas_per_capture][1024]                               */
-    uint32_t ctas_per_capture;
+    float *partials;          /* [capture][units_per_capture][1024]                              */
+    uint32_t units_per_capture; /* ceil(frames / (4 frames_per_warp))                            */
+    uint32_t total_units;     /* n_captures x units_per_capture; CTA b takes units b, b + gridDim.x, ... */
     float ema_log2_decay;     /* log2(1 - beta), EMA only                                        */
     float ema_beta;
 };
@@ -136,17 +140,6 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
     __syncthreads();
     const cvt_k cb = b200_cvt_consts_load(s_cvt);
 
-    const uint32_t capture = blockIdx.y;
-    const uint32_t warp_global = blockIdx.x * B200_SPEC_WARPS + (uint32_t)warp;
-    const uint32_t m_begin = warp_global * p.frames_per_warp;
-    uint32_t m_end = m_begin + p.frames_per_warp;
-    if (m_end > p.frames) m_end = p.frames;
-
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
-
-    const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
     const float *my_win = s_win + lane * B200_SPEC_WP;
 #if B200_SPEC_EXPERIMENT & 3
     const float fake_w = my_win[0] + 0.5f;
@@ -162,8 +155,21 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
     for (int i = 0; i < 8; ++i) r_win[i] = *reinterpret_cast<const float4 *>(my_win + 4 * i);
 #endif
 
+    float *s_red = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_XP); /* [warp][1024], pitch 32*XP*2 floats */
+    for (uint32_t unit_g = blockIdx.x; unit_g < p.total_units; unit_g += gridDim.x) {
+    const uint32_t capture = unit_g / p.units_per_capture;
+    const uint32_t warp_global = (unit_g - capture * p.units_per_capture) * B200_SPEC_WARPS + (uint32_t)warp;
+    const uint32_t m_begin = warp_global * p.frames_per_warp;
+    uint32_t m_end = m_begin + p.frames_per_warp;
+    if (m_end > p.frames) m_end = p.frames;
+
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+
+    const uint8_t *cap = p.iq + (uint64_t)capture * p.capture_stride;
     /* software pipeline: the 32 two-byte loads of frame m+1 are issued before the FFT of frame m,
-     * so no warp ever waits on HBM/L2 latency with only three warps per scheduler resident */
+     * so no warp ever waits on HBM/L2 latency with only two warps per scheduler resident */
     const unsigned short *src0 = reinterpret_cast<const unsigned short *>(cap) + (uint32_t)lane;
     uint32_t raw[32];
     if (B200_SPEC_PREFETCH && m_begin < m_end) {
@@ -283,32 +289,34 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         }
     }
 
-    /* fixed-order reduction over the CTA's warps, then one partial per CTA */
+    /* fixed-order reduction over the unit's four warps, then one partial per unit (the reduction buffer
+     * aliases the transpose tiles: barriers on both sides) */
     __syncthreads();
-    float *s_red = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_XP); /* [warp][1024], pitch 32*XP*2 floats */
     float *mine = s_red + warp * (32 * B200_SPEC_XP * 2);
 #pragma unroll
     for (int k2 = 0; k2 < 32; ++k2) mine[k2 * 32 + lane] = acc[k2]; /* bin k = lane + 32 k2 */
     __syncthreads();
-    float *out = p.partials + ((uint64_t)capture * p.ctas_per_capture + blockIdx.x) * 1024u;
+    float *out = p.partials + (uint64_t)unit_g * 1024u;
     for (int k = tid; k < 1024; k += B200_SPEC_THREADS) {
         float s = 0.0f;
 #pragma unroll
         for (int w = 0; w < B200_SPEC_WARPS; ++w) s += s_red[w * (32 * B200_SPEC_XP * 2) + k];
         out[k] = s;
     }
+    __syncthreads();
+    } /* units */
 }
 
 /* out[c][k] = scale * sum_i partials[c][i][k] + carry_scale * carry[k]  (fixed order) */
-__global__ void __launch_bounds__(256) k_spectrum_finalize(const float *partials, uint32_t ctas_per_capture,
+__global__ void __launch_bounds__(256) k_spectrum_finalize(const float *partials, uint32_t units_per_capture,
                                                            float scale, const float *carry, float carry_scale,
                                                            float *out)
 {
     const uint32_t capture = blockIdx.y;
     const uint32_t k = blockIdx.x * 256u + threadIdx.x;
-    const float *src = partials + (uint64_t)capture * ctas_per_capture * 1024u + k;
+    const float *src = partials + (uint64_t)capture * units_per_capture * 1024u + k;
     float s = 0.0f;
-    for (uint32_t i = 0; i < ctas_per_capture; ++i) s += src[(uint64_t)i * 1024u];
+    for (uint32_t i = 0; i < units_per_capture; ++i) s += src[(uint64_t)i * 1024u];
     float r = s * scale;
     if (carry) r = fmaf(carry[(uint64_t)capture * 1024u + k], carry_scale, r);
     out[(uint64_t)capture * 1024u + k] = r;

@@ -34,11 +34,14 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
     p.window = window;
     p.twiddle = tw.data();
     p.partials = partials.data();
-    p.ctas_per_capture = ctas;
+    p.units_per_capture = ctas;
+    p.total_units = ctas * n_captures;
     p.ema_beta = beta;
     p.ema_log2_decay = log2f(1.0f - beta);
-    if (ema) emu::launch(dim3(ctas, n_captures), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<true>(p); });
-    else emu::launch(dim3(ctas, n_captures), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<false>(p); });
+    /* a persistent grid smaller than the number of units: every CTA walks several units */
+    const uint32_t grid = p.total_units > 3 ? 3 : p.total_units;
+    if (ema) emu::launch(dim3(grid), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<true>(p); });
+    else emu::launch(dim3(grid), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<false>(p); });
     float scale = ema ? 1.0f : 1.0f / (float)frames;
     emu::launch(dim3(4, n_captures), dim3(256), 0,
                 [&] { k_spectrum_finalize(partials.data(), ctas, scale, nullptr, 0.0f, out); });
@@ -109,13 +112,14 @@ int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, v
 
 int emu_sizeof_fm_state(void) { return (int)sizeof(FmState); }
 
-/* the product's spectrum launch plan (csrc/plan.h): out3 = frames, frames_per_warp, ctas_per_capture */
-void emu_plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count, uint32_t *out3)
+/* the product's spectrum launch plan (csrc/plan.h): out4 = frames, frames_per_warp, units_per_capture, grid */
+void emu_plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count, uint32_t *out4)
 {
     const b200::SpectrumPlan pl = b200::plan_spectrum(len_bytes, n_captures, sm_count);
-    out3[0] = pl.frames;
-    out3[1] = pl.frames_per_warp;
-    out3[2] = pl.ctas_per_capture;
+    out4[0] = pl.frames;
+    out4[1] = pl.frames_per_warp;
+    out4[2] = pl.units_per_capture;
+    out4[3] = pl.grid;
 }
 
 /* K2 conversion (window may be NULL) as b200sdr_convert_cf32_dev launches it; len_bytes % 16 == 0 */

@@ -38,26 +38,29 @@ def padded(a):
 
 
 def test_spectrum_launch_plan(emu):
-    """csrc/plan.h plan_spectrum: every frame is covered exactly once, and the cost model picks long warps
-    for big batches (few partial sums), mid-sized ones for a single capture (one wave of CTAs, prologue
-    amortised) and one frame per warp for a small streaming block (all SMs busy)."""
+    """csrc/plan.h plan_spectrum: every frame is covered exactly once; frames per warp (hence the summation
+    tree, hence the bits of a capture's spectrum) depend on the capture LENGTH only -- not on the batch size,
+    not on the device; the persistent grid never exceeds the resident CTA slots."""
     emu.emu_plan_spectrum.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
 
     def plan(nbytes, ncap, sms=148):
-        out = (C.c_uint32 * 3)()
+        out = (C.c_uint32 * 4)()
         emu.emu_plan_spectrum(nbytes, ncap, sms, out)
         return tuple(out)
 
     for nbytes, ncap in ((48_000_000, 512), (48_000_000, 96), (48_000_000, 4), (48_000_000, 1), (262144, 1),
-                         (2048, 1), (2048 + 1024 * 5, 3), (4 * 262144, 7), (48_000_000, 65535)):
-        frames, fpw, ctas = plan(nbytes, ncap)
+                         (2048, 1), (2048 + 1024 * 5, 3), (4 * 262144, 7), (48_000_000, 65535), (480_000_000, 2)):
+        frames, fpw, units, grid = plan(nbytes, ncap)
         assert frames == (nbytes // 2 - 1024) // 512 + 1
-        assert 1 <= fpw <= 256 and (ctas - 1) * fpw * 4 < frames <= ctas * fpw * 4   # no empty CTA, all frames covered
-    assert plan(2046, 1) == (0, 0, 0)                      # shorter than one frame: nothing to launch
-    assert plan(48_000_000, 512)[1] >= 200                 # big batch: <= 60 partial sums per capture
-    assert 30 <= plan(48_000_000, 1)[1] <= 64              # one capture: ~one wave of 296 CTAs
-    assert plan(262144, 1)[1] == 1                         # one 256 KiB block: 64 CTAs of 4 single-frame warps
-    assert plan(48_000_000, 1, 74)[1] > plan(48_000_000, 1, 148)[1]   # fewer SMs -> longer warps
+        assert 1 <= fpw <= 64 and (units - 1) * fpw * 4 < frames <= units * fpw * 4   # no empty unit, all frames covered
+        assert 1 <= grid <= min(units * ncap, 2 * 148)
+        for other_ncap, sms in ((1, 148), (8, 148), (512, 148), (4096, 74), (3, 132)):
+            assert plan(nbytes, other_ncap, sms)[:3] == (frames, fpw, units)           # batch-shape / device independent
+    assert plan(2046, 1) == (0, 0, 0, 0)                   # shorter than one frame: nothing to launch
+    assert plan(48_000_000, 1)[1:] == (40, 293, 293)       # one 10 s capture: one wave of 296 CTA slots
+    assert plan(48_000_000, 512)[3] == 296                 # a batch: persistent grid, 293 x 512 units
+    assert plan(262144, 1)[1:] == (1, 64, 64)              # one 256 KiB block: 64 CTAs of 4 single-frame warps
+    assert plan(480_000_000, 1)[1] == 64                   # long captures: capped (partials < 2 % of the input)
 
 
 def test_convert_and_generator_kernels(emu, g):

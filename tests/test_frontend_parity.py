@@ -35,8 +35,8 @@ def test_kats_from_the_survey(b):
 
 
 def test_unsupported_rates_are_reported(b):
-    for rate in (225000, 300001, 900000, 3200001):
-        assert b.rtl_resampler(rate)[0] == 3  # B200SDR_NOT_SUPPORTED
+    for rate in (225000, 300001, 900000, 3200001, 28125, 1):
+        assert b.rtl_resampler(rate) == (3, 0, 0, 0.0)  # B200SDR_NOT_SUPPORTED, outputs zeroed
     for rate in (225001, 300000, 900001, 3200000):
         assert b.rtl_resampler(rate)[0] == 0
 
@@ -57,7 +57,10 @@ def test_resampler_bit_exact_against_reference(b):
     rates += [int(x) for x in np.random.default_rng(0).integers(226000, 3200000, 40)]
     for rate in rates:
         a, r, real = ref("--rate", rate)
-        _, ratio, applied, real_rate = b.rtl_resampler(rate)
+        rc, ratio, applied, real_rate = b.rtl_resampler(rate)
+        if rc != 0:   # a rate the chip cannot take (300 001 .. 900 000): reported, outputs zeroed, nothing to compare
+            assert 300000 < rate <= 900000 and (rc, ratio, applied, real_rate) == (3, 0, 0, 0.0)
+            continue
         assert (ratio, applied) == (int(a), int(r)), rate
         assert real_rate == float(real), rate  # %.17g round-trips a double exactly
 
@@ -161,10 +164,12 @@ def test_init_sequence_shape_and_errors(b):
     assert rc == 0 and n == 108
     assert bytes(rec2[(rec2["v"] == 0x9F20) & (rec2["t"] == 0x40)][0]["d"]) == b"\x03\x00"
     assert rec2[(rec2["step"] == 31) & (rec2["t"] == 0x40)][0]["d"][0] == 0x05
-    # capacity too small: count still reported, BUSY; unsupported rate: NOT_SUPPORTED, list still produced
+    # capacity too small: count still reported, BUSY; unsupported rate / FIR: NOT_SUPPORTED and nothing emitted
     assert b.rtl_init_sequence(capacity=10)[:2] == (1, 108)
     assert b.rtl_init_sequence(capacity=0)[:2] == (1, 108)
-    assert b.rtl_init_sequence(500000)[:2] == (3, 108)
+    assert b.rtl_init_sequence(500000)[:2] == (3, 0)
+    assert b.rtl_init_sequence(20000)[:2] == (3, 0)      # quotient would not fit 32 bits: rejected before the cast
+    assert b.rtl_init_sequence(240000, fir=[4000] * 16)[:2] == (3, 0)
     assert b.rtl_init_sequence(0)[0] == 2
 
 

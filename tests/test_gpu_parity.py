@@ -698,3 +698,88 @@ def test_contexts_are_independent(sdr_lib, g):
     finally:
         for s in ctxs:
             s.close()
+
+
+# ------------------------------------------------------------- multi-GPU sharding
+def _run_shards(pkg, devices, iq, n_cap, len_each, shards):
+    """Every shard (lo, hi) of the batch on its own context (round-robin over `devices`); per-capture
+    spectra / WBFM audio / AM audio gathered in capture order."""
+    spec, fm, am = [], [], []
+    ctxs = [pkg.B200Sdr(device=d) for d in devices]
+    try:
+        for i, (lo, hi) in enumerate(shards):
+            if hi <= lo:
+                continue
+            s = ctxs[i % len(ctxs)]
+            part = iq[lo * len_each:hi * len_each]
+            spec.append(s.spectrum(part, hi - lo))
+            fm.append(s.wbfm(part, hi - lo))
+            am.append(s.am(part, hi - lo))
+    finally:
+        for s in ctxs:
+            s.close()
+    return np.concatenate(spec), np.concatenate(fm), np.concatenate(am)
+
+
+@pytest.mark.parametrize("len_each", [262144, 16 * 190_000 + 16], ids=["block_256KiB", "3MB_capture"])
+def test_sharded_batch_is_bitwise_the_single_context_batch(sdr_lib, g, len_each):
+    """configs[4] shards 4096 captures over 1/2/4/8 GPUs.  A capture's results must not depend on which
+    captures share its launch or on which GPU runs it: the same batch as ONE launch, as 2 / 4 / 8
+    contiguous shards (stm32f7-rtlsdr_b200/sharding.py, the partition bench.py uses) and one capture at a time --
+    on two devices when the box has them, else on two contexts of one -- gives bitwise equal spectra and audio.
+    (The spectrum's summation tree follows from the capture length only, csrc/plan.h.)"""
+    sharding = __import__("importlib").import_module("stm32f7-rtlsdr_b200.sharding")
+    n_dev = 1
+    try:
+        import torch
+        n_dev = max(1, torch.cuda.device_count())
+    except Exception:
+        pass
+    n_cap = 16
+    iq = np.concatenate([g.synth(1, len_each, (SYNTH_MULTITONE, SYNTH_WBFM, SYNTH_AM)[c % 3], 300 + c) for c in range(n_cap)])
+    whole = _run_shards(sdr_lib, [0], iq, n_cap, len_each, [(0, n_cap)])
+    gold, frames = g.spectrum(iq[:len_each])
+    spec_check(whole[0][0], gold) if frames >= 200 else spec_check_few_frames(whole[0][0], gold)
+    for world in (2, 4, 8, n_cap):
+        devices = list(range(min(n_dev, 2))) if n_dev > 1 else [0, 0]
+        got = _run_shards(sdr_lib, devices, iq, n_cap, len_each, sharding.all_shards(n_cap, world))
+        for name, a, b in zip(("spectrum", "wbfm", "am"), whole, got):
+            assert a.shape == b.shape and np.array_equal(a, b), f"{name}: {world} shards differ from the single batch"
+
+
+def test_full_size_capture_alone_equals_in_batch(sdr, g):
+    """Same at BASELINE's full size: a 10 s capture alone vs inside a batch of 5 (different neighbours)."""
+    n_cap, len_each = 5, 48_000_000
+    na = 480000
+    d_iq = sdr.dev_alloc(n_cap * len_each)
+    d_spec, d_fm = sdr.dev_alloc(4 * 1024 * (n_cap + 1)), sdr.dev_alloc(4 * na * (n_cap + 1))
+    try:
+        for c in range(n_cap):
+            sdr.synth_fill_dev(d_iq + c * len_each, 1, len_each, SYNTH_WBFM if c % 2 else SYNTH_MULTITONE, first_capture=2000 + c)
+        sdr.batch_spectrum_dev(d_iq, n_cap, len_each, d_spec)
+        sdr.batch_wbfm_dev(d_iq, n_cap, len_each, d_fm)
+        sdr.sync()
+        spec = sdr.to_host(d_spec, 4 * 1024 * n_cap, np.float32).reshape(n_cap, 1024)
+        fm = sdr.to_host(d_fm, 4 * na * n_cap, np.float32).reshape(n_cap, na)
+        for c in (0, 3, 4):
+            sdr.batch_spectrum_dev(d_iq + c * len_each, 1, len_each, d_spec + 4 * 1024 * n_cap)
+            sdr.batch_wbfm_dev(d_iq + c * len_each, 1, len_each, d_fm + 4 * na * n_cap)
+            sdr.sync()
+            assert np.array_equal(sdr.to_host(d_spec + 4 * 1024 * n_cap, 4 * 1024, np.float32), spec[c])
+            assert np.array_equal(sdr.to_host(d_fm + 4 * na * n_cap, 4 * na, np.float32), fm[c])
+    finally:
+        for p in (d_iq, d_spec, d_fm):
+            sdr.dev_free(p)
+
+
+def test_one_big_slot_fits_a_small_audio_fifo(sdr_lib, g):
+    """slot_bytes = 1 MiB with audio_capacity = 4096 used to answer BUSY for ever (one slot makes
+    10 486 WBFM samples); b200sdr_create now raises the FIFO to what one full slot produces."""
+    blk = 1 << 20
+    iq = g.synth(1, blk, SYNTH_WBFM, 5)
+    with sdr_lib.B200Sdr(slot_bytes=blk, ring_slots=2, audio_capacity=4096) as s:
+        assert s.process_samples(iq, allow_busy=True) == sdr_lib.OK
+        fm = s.get_audio(sdr_lib.CHAIN_WBFM)
+        n_fm = -(-((blk // 2 // 120) * 12) // 5)
+        assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
+        assert s.process_samples(iq, allow_busy=True) == sdr_lib.OK     # and again after the pop

@@ -1,5 +1,11 @@
-"""Print the metrics that matter from an .ncu-rep (raw page): used to write profiles/*.txt"""
-import csv, subprocess, sys
+"""Print the metrics that matter from an .ncu-rep (raw page): used to write profiles/*.txt
+
+    python tools/ncu_summary.py <file.ncu-rep>                      metrics of every captured launch
+    python tools/ncu_summary.py <file.ncu-rep> --traffic KEY ALGORITHMIC_BYTES [SOURCE]
+        additionally records dram__bytes_read.sum + dram__bytes_write.sum of the first launch under KEY in
+        profiles/ncu_traffic.json, the tracked file bench.py takes `roofline.traffic` from (no literal in bench.py).
+"""
+import csv, json, os, subprocess, sys
 WANT = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
  'sm__throughput.avg.pct_of_peak_sustained_elapsed','sm__inst_executed.sum','smsp__inst_executed.sum','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
  'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
@@ -24,3 +30,26 @@ for V in rows[2:]:
     for w in WANT:
         if w in H:
             i=H.index(w); print(f'  {w:92s} {V[i]:>16s} {U[i]}')
+
+
+def _bytes(v, unit):
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+    return float(v.replace(",", "")) * mult
+
+
+if "--traffic" in sys.argv:
+    a = sys.argv.index("--traffic")
+    key, algo = sys.argv[a + 1], float(sys.argv[a + 2])
+    source = sys.argv[a + 3] if len(sys.argv) > a + 3 else os.path.basename(sys.argv[1])
+    V = rows[2]
+    rd = _bytes(V[H.index("dram__bytes_read.sum")], U[H.index("dram__bytes_read.sum")])
+    wr = _bytes(V[H.index("dram__bytes_write.sum")], U[H.index("dram__bytes_write.sum")])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+    except OSError:
+        d = {}
+    d[key] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr, "algorithmic_bytes": algo,
+              "ratio": (rd + wr) / algo, "source": source}
+    json.dump(d, open(path, "w"), indent=1)
+    print("traffic", key, d[key])
