@@ -76,6 +76,7 @@ struct b200sdr_ctx {
 
     /* workspaces (grown on demand) */
     float *d_partials = nullptr; size_t partials_floats = 0;
+    uint32_t *d_unit_counter = nullptr; /* k_spectrum: dynamic hand-out of work units (two words, self-resetting) */
     float *d_env = nullptr; size_t env_floats = 0;
     float *d_res_spec = nullptr, *d_res_fm = nullptr, *d_res_am = nullptr; /* batch_host result staging */
     size_t res_spec_floats = 0, res_fm_floats = 0, res_am_floats = 0;
@@ -176,6 +177,7 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     p.partials = ctx->d_partials;
     p.units_per_capture = pl.units_per_capture;
     p.total_units = (uint32_t)pl.total_units;
+    p.unit_counter = ctx->d_unit_counter;
     p.ema_beta = ctx->cfg.ema_beta;
     p.ema_log2_decay = log2f(1.0f - ctx->cfg.ema_beta);
     dim3 grid(pl.grid);
@@ -638,6 +640,8 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
         CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
     }
     CK(cudaMalloc((void **)&ctx->d_spec_acc, 1024 * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->d_unit_counter, 2 * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_unit_counter, 0, 2 * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_cnt_state, sizeof(CounterStreamState)));
     CK(cudaMalloc((void **)&ctx->d_fm_state, 2 * sizeof(FmState)));
     CK(cudaMalloc((void **)&ctx->d_amf_state, 2 * sizeof(AmFrontState)));
@@ -680,7 +684,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
-    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc,
+    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc, ctx->d_unit_counter,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,

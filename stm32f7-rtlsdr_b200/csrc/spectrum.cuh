@@ -25,8 +25,12 @@
  * results, no float atomics.  frames_per_warp follows from the capture LENGTH only (plan.h), so the
  * summation tree of a capture -- hence every bit of its spectrum -- is the same whether the capture is
  * processed alone, in a batch of 512 or in a 4096 / N shard on another GPU.  The grid is persistent
- * (one CTA per resident slot, CTA b takes units b, b + grid, ...): the per-CTA prologue (constants to
- * registers) is paid once however short the units are.
+ * (one CTA per resident slot): the per-CTA prologue (constants to registers) is paid once however short
+ * the units are.  Units are handed out DYNAMICALLY (CTA b starts with unit b, every further one comes from
+ * an atomic counter): the two warps that share a scheduler do not get equal shares of it, so with a static
+ * split one CTA of every SM finished early and left the other alone on the SM for the last quarter of the
+ * kernel -- 11 % slower than handing out units as CTAs become free (measured, profiles/r2_spectrum_units.txt).
+ * Which CTA computes a unit never changes its partial, so results stay deterministic.
  *
  * Input access: lane t reads the 2-byte sample n = t + 32 j straight from global memory
  * (a warp reads 64 contiguous bytes per j; both halves of every 128-byte line are used by
@@ -102,7 +106,9 @@ struct SpectrumParams {
     const float2 *twiddle;    /* 1024 entries: e^{-2 pi i m / 1024}                              */
     float *partials;          /* [capture][units_per_capture][1024]                              */
     uint32_t units_per_capture; /* ceil(frames / (4 frames_per_warp))                            */
-    uint32_t total_units;     /* n_captures x units_per_capture; CTA b takes units b, b + gridDim.x, ... */
+    uint32_t total_units;     /* n_captures x units_per_capture                                  */
+    uint32_t *unit_counter;   /* two words, zero before the first launch: [0] units handed out beyond the first
+                                 gridDim.x, [1] CTAs finished (the last one leaves both at zero again)     */
     float ema_log2_decay;     /* log2(1 - beta), EMA only                                        */
     float ema_beta;
 };
@@ -156,7 +162,10 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
 #endif
 
     float *s_red = reinterpret_cast<float *>(smem + B200_SPEC_SMEM_XP); /* [warp][1024], pitch 32*XP*2 floats */
-    for (uint32_t unit_g = blockIdx.x; unit_g < p.total_units; unit_g += gridDim.x) {
+    uint32_t unit_g = blockIdx.x;
+    while (unit_g < p.total_units) {
+    /* ask for the next unit now; the answer is read after this unit's barriers */
+    if (tid == 0) s_cvt[2] = gridDim.x + atomicAdd(p.unit_counter, 1u);
     const uint32_t capture = unit_g / p.units_per_capture;
     const uint32_t warp_global = (unit_g - capture * p.units_per_capture) * B200_SPEC_WARPS + (uint32_t)warp;
     const uint32_t m_begin = warp_global * p.frames_per_warp;
@@ -303,8 +312,11 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         for (int w = 0; w < B200_SPEC_WARPS; ++w) s += s_red[w * (32 * B200_SPEC_XP * 2) + k];
         out[k] = s;
     }
-    __syncthreads();
+    unit_g = s_cvt[2];
+    __syncthreads(); /* the reduction buffer and s_cvt[2] are free again */
     } /* units */
+    /* the last CTA out leaves the hand-out counter at zero for the next launch (atomicInc wraps its own word) */
+    if (tid == 0 && atomicInc(p.unit_counter + 1, gridDim.x - 1u) == gridDim.x - 1u) p.unit_counter[0] = 0u;
 }
 
 /* out[c][k] = scale * sum_i partials[c][i][k] + carry_scale * carry[k]  (fixed order) */

@@ -279,5 +279,6 @@ static inline float2 __ldg(const float2 *p) { return *p; }
 static inline float4 __ldg(const float4 *p) { return *p; }
 static inline float atomicAdd(float *p, float v) { float o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline unsigned atomicInc(unsigned *p, unsigned wrap) { unsigned o = *p; *p = (o >= wrap) ? 0u : o + 1u; return o; }
 
 #endif

@@ -36,6 +36,8 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
     p.partials = partials.data();
     p.units_per_capture = ctas;
     p.total_units = ctas * n_captures;
+    uint32_t unit_counter[2] = {0u, 0u};
+    p.unit_counter = unit_counter;
     p.ema_beta = beta;
     p.ema_log2_decay = log2f(1.0f - beta);
     /* a persistent grid smaller than the number of units: every CTA walks several units */
@@ -43,6 +45,7 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
     if (ema) emu::launch(dim3(grid), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<true>(p); });
     else emu::launch(dim3(grid), dim3(B200_SPEC_THREADS), B200_SPEC_SMEM_BYTES, [&] { k_spectrum<false>(p); });
     float scale = ema ? 1.0f : 1.0f / (float)frames;
+    if (unit_counter[0] != 0u || unit_counter[1] != 0u) return -2; /* the last CTA must leave the hand-out counter at zero */
     emu::launch(dim3(4, n_captures), dim3(256), 0,
                 [&] { k_spectrum_finalize(partials.data(), ctas, scale, nullptr, 0.0f, out); });
     return (int)frames;

@@ -8,7 +8,7 @@ cp $LIB build/variants/original.so
 for so in $(ls build/variants/[0-9]*.so | sort -V); do
   v=$(cat ${so%.so}.flags)
   cp $so $LIB
-  timeout 600 python bench.py --steps 3 --warmup 3 --captures-per-gpu ${VCAPS:-96} --e2e-captures 4 --no-cpu-baseline > gpurun_out/bench_var.txt 2>&1
+  timeout 600 python bench.py --steps 3 --warmup 3 --captures-per-gpu ${VCAPS:-96} --e2e-captures 4 --config4-waves 0 --parity-captures 4 --no-cpu-baseline > gpurun_out/bench_var.txt 2>&1
   python - "$v" <<'PY' >> gpurun_out/variants.txt
 import json, sys
 try:
