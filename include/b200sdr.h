@@ -207,6 +207,11 @@ B200SDR_API uint64_t b200sdr_spectrum_frames(uint64_t len_bytes);  /* floor((L-1
 B200SDR_API uint64_t b200sdr_wbfm_disc_len(uint64_t len_bytes);    /* ceil(L/10)                          */
 B200SDR_API uint64_t b200sdr_wbfm_audio_len(uint64_t len_bytes);   /* ceil(ceil(L/10)/5)                  */
 B200SDR_API uint64_t b200sdr_am_audio_len(uint64_t len_bytes);     /* ceil(2*ceil(ceil(L/20)/10)/3)       */
+/* Streaming granularity of a demodulator chain (B200SDR_CHAIN_WBFM / _AM) in complex samples: the streaming
+ * path consumes whole chunks, what is left of a block (< one chunk) waits for the next block.  After n
+ * accepted samples the audio FIFO has received ceil(floor(n / chunk) * (chunk / 10) / 5) WBFM samples
+ * (AM: (2 floor(n / chunk) + 2) / 3).  0 for a chain without audio output. */
+B200SDR_API uint32_t b200sdr_stream_chunk_samples(uint32_t chain);
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone IQ conversion (kernel K2): out[2n] = (I_n - 127.5) * w[n mod 1024],

@@ -36,6 +36,8 @@ from .binding import (  # noqa: F401
     spectrum_frames,
     wbfm_disc_len,
     wbfm_audio_len,
+    wbfm_stream_audio_len,
+    stream_chunk_samples,
     am_audio_len,
     synth_fill_host,
 )

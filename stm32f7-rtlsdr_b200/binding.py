@@ -83,6 +83,7 @@ def load_library():
         "b200sdr_wbfm_disc_len": (u64, [u64]),
         "b200sdr_wbfm_audio_len": (u64, [u64]),
         "b200sdr_am_audio_len": (u64, [u64]),
+        "b200sdr_stream_chunk_samples": (u32, [u32]),
         "b200sdr_convert_cf32": (i32, [vp, u8p, u32, u32, f32p]),
         "b200sdr_convert_cf32_dev": (i32, [vp, u8p, u64, u32, f32p]),
         "b200sdr_counter_check_dev": (i32, [vp, u8p, u32, u64, C.c_int32, C.POINTER(u64), C.POINTER(u64)]),
@@ -127,6 +128,16 @@ def wbfm_audio_len(len_bytes):
 
 def am_audio_len(len_bytes):
     return int(load_library().b200sdr_am_audio_len(len_bytes))
+
+
+def stream_chunk_samples(chain):
+    return int(load_library().b200sdr_stream_chunk_samples(chain))
+
+
+def wbfm_stream_audio_len(total_bytes):
+    """WBFM audio samples the streaming path has produced after `total_bytes` accepted bytes (whole chunks only)."""
+    ch = stream_chunk_samples(CHAIN_WBFM)
+    return -(-((total_bytes // 2 // ch) * (ch // 10)) // 5)
 
 
 def synth_fill_host(n_captures, len_each, kind, first_capture=0):

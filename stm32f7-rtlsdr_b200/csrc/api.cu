@@ -849,6 +849,10 @@ uint64_t b200sdr_spectrum_frames(uint64_t len_bytes) { return b200::spectrum_fra
 uint64_t b200sdr_wbfm_disc_len(uint64_t len_bytes) { return b200::wbfm_disc_len(len_bytes); }
 uint64_t b200sdr_wbfm_audio_len(uint64_t len_bytes) { return b200::wbfm_audio_len(len_bytes); }
 uint64_t b200sdr_am_audio_len(uint64_t len_bytes) { return b200::am_audio_len(len_bytes); }
+uint32_t b200sdr_stream_chunk_samples(uint32_t chain)
+{
+    return chain == B200SDR_CHAIN_WBFM ? B200_FM_CHUNK : chain == B200SDR_CHAIN_AM ? B200_AM_CHUNK : 0u;
+}
 
 int32_t b200sdr_batch_spectrum_dev(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_each,
                                    float *spectrum_dev)

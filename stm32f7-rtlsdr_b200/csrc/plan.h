@@ -81,8 +81,8 @@ inline FmPlan plan_wbfm_batch(uint64_t len_bytes, uint32_t n_captures, uint32_t 
     pl.m1 = ceil_div(n, 10);
     pl.total_chunks = (uint32_t)ceil_div(n, B200_FM_CHUNK);
     pl.n_tiles = (uint32_t)ceil_div(pl.total_chunks, B200_FM_THREADS);
-    /* many equal segments (>= ~10 waves of CTAs at 4 CTAs per SM, so the last partial wave is
-     * small) but never shorter than 16 tiles: segments > 0 re-run one tile as pre-roll */
+    /* many equal segments (>= ~10 waves of CTAs, so the last partial wave is small) but never shorter
+     * than 16 tiles: segments > 0 re-run one tile as pre-roll */
     uint64_t want = ceil_div((uint64_t)sm_count * 40, n_captures ? n_captures : 1);
     uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
     if (tps < 16) tps = 16;
@@ -113,7 +113,7 @@ inline void fill_fm_taps(FmTaps &t)
     for (int k = 0; k < B200_FM_T2; ++k) t.h2[k] = (float)h2[k];
     const double alpha = deemph_alpha(), a = 1.0 - alpha;
     t.alpha = (float)alpha;
-    for (int i = 0; i < 16; ++i) t.apow[i] = (float)std::pow(a, i + 1);
+    for (int i = 0; i < 32; ++i) t.apow[i] = (float)std::pow(a, i + 1);
     const double a12 = std::pow(a, B200_FM_OPT);
     t.a12 = (float)a12;
     for (int s = 0; s < 5; ++s) t.a12pow[s] = (float)std::pow(a12, double(1 << s));

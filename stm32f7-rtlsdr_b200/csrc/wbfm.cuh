@@ -8,29 +8,32 @@
  * (RTL/Inc/usbh_rtlsdr.h:340-345) runs before the bytes reach us.  Definition followed:
  * oracle/golden.c gold_wbfm().
  *
- * Work split.  grid = (segments, captures).  A CTA of 128 threads walks the tiles of its segment
- * in order; a tile is 128 x 120 input samples (30 720 bytes) brought in by one TMA bulk copy into a
- * single buffer that is re-armed as soon as the FIR has consumed it (4 CTAs per SM overlap the rest).
+ * Work split.  grid = (segments, captures).  A CTA of B200_FM_THREADS threads walks the tiles of its segment
+ * in order; a tile is THREADS x 200 input samples brought in by one TMA bulk copy into a single buffer that
+ * is re-armed as soon as the FIR has consumed it (the other CTAs of the SM overlap the rest).
+ * A thread's chunk is 200 samples = 20 stage-1 outputs = exactly 4 audio samples, so every stage is balanced
+ * over all threads and the /5 FIR reads its window of e[] with aligned 128-bit loads at a fixed offset.
  *
- * Stage 1 is written "input-partitioned": thread t owns input samples [a, a+120), a = tile + 120 t,
+ * Stage 1 is written "input-partitioned": thread t owns input samples [a, a+200), a = tile + 200 t,
  * turns each byte pair into a pair of floats exactly once -- two PRMTs and no arithmetic: the bytes are read
  * as raw (sub)normal floats u * 2^-133 and the -127.5 offset is carried by the accumulators' start values,
  * cplx2.cuh form C -- and scatters it into the (at most
  * 8) outputs y1[m] = sum_k h[k] x[10 m - k] whose window covers it.  Eight packed accumulators
  * rotate; output i of the chunk (centre a + 10 i) completes at sample 10 i:
  *     i = 0..7   partially complete ("heads", started in the previous thread's chunk)
- *     i = 8..11  complete inside the chunk
- *     i = 12..19 started here, finished by the next thread  ("tails", 8 partial sums)
+ *     i = 8..19  complete inside the chunk
+ *     i = 20..27 started here, finished by the next thread  ("tails", 8 partial sums)
  * Thread t+1 adds thread t's tails to its heads through shared memory; the last thread's tails
  * are carried to the next tile.  So the FIR needs NO input history at all -- a capture (or a
  * stream) starts with the start-of-stream tails (FmTaps::bias_head), which is exactly x[n<0] = 0 -- and
  * costs exactly 8 packed FMAs per input sample with taps held in registers (40 distinct: the filter is
  * symmetric).
  *
- * The 240 kS/s stages run per tile on the 1536 fresh outputs: discriminator (atan2 of
- * y[m] conj(y[m-1])), the de-emphasis recurrence as a fixed-shape scan (thread-serial over 12,
+ * The 240 kS/s stages run per tile on the fresh outputs: discriminator (atan2 of
+ * y[m] conj(y[m-1])), the de-emphasis recurrence as a fixed-shape scan (thread-serial over 20,
  * warp shuffle scan, cross-warp carry, exact carried state between tiles), then the /5 FIR out
- * of a shared-memory window with 49 samples of history.
+ * of a shared-memory window with 49 samples of history (taps outermost: each tap is fetched once
+ * for the thread's four outputs).
  *
  * Segments after the first start one tile early with stores suppressed: that warms the carried
  * state up (de-emphasis pole 0.946^1536 ~ 0).  Segment 0 and the streaming path (`state` != 0)
@@ -42,19 +45,25 @@
 #include "cplx2.cuh"
 #include "tma.cuh"
 
+#ifndef B200_FM_THREADS
 #define B200_FM_THREADS 128
-#define B200_FM_CHUNK 120                                  /* input samples per thread per tile      */
-#define B200_FM_OPT 12                                     /* stage-1 outputs per thread per tile    */
-#define B200_FM_TILE_IN (B200_FM_THREADS * B200_FM_CHUNK)  /* 15360                                  */
-#define B200_FM_TILE_OUT (B200_FM_THREADS * B200_FM_OPT)   /* 1536                                   */
-#define B200_FM_TILE_BYTES (2 * B200_FM_TILE_IN)           /* 30720                                  */
+#endif
+#ifndef B200_FM_MINB
+#define B200_FM_MINB (B200_FM_THREADS == 128 ? 3 : 6)      /* CTAs per SM (shared memory: 71 KB / 37 KB per CTA) */
+#endif
+#define B200_FM_WARPS (B200_FM_THREADS / 32)
+#define B200_FM_CHUNK 200                                  /* input samples per thread per tile      */
+#define B200_FM_OPT 20                                     /* stage-1 outputs per thread per tile    */
+#define B200_FM_TILE_IN (B200_FM_THREADS * B200_FM_CHUNK)  /* 25600 (128 threads)                    */
+#define B200_FM_TILE_OUT (B200_FM_THREADS * B200_FM_OPT)   /* 2560                                   */
+#define B200_FM_TILE_BYTES (2 * B200_FM_TILE_IN)           /* 51200                                  */
 #define B200_FM_T1 80
 #define B200_FM_T2 50
 #define B200_FM_D2 5
 #define B200_FM_HIST (B200_FM_T2 - 1) /* 49 */
 #define B200_FM_HPAD 52               /* history slots before the tile's e[] (16-byte aligned)        */
-#define B200_FM_TAILP 132             /* pitch (in c2) of one row of the transposed tail exchange     */
-#define B200_FM_APT 3                 /* consecutive audio samples per thread in stage 2              */
+#define B200_FM_TAILP (B200_FM_THREADS + 4) /* pitch (in c2) of one row of the transposed tail exchange */
+#define B200_FM_APT 4                 /* consecutive audio samples per thread in stage 2 (= OPT / D2) */
 
 /* shared memory carve-up.  ONE raw buffer: the TMA copy of tile t+1 is issued as soon as the
  * scatter FIR of tile t has consumed it and lands while the 240 kS/s stages run, so four CTAs
@@ -96,11 +105,11 @@ struct FmTaps {
     float bias_head[8];    /* -127.5 sum_{k <= 10 i} h1[k]: carried-in part of outputs 0..7 of a stream, whose
                               own part starts from zero (x[n < 0] = 0; small and exact)                       */
     float h2[B200_FM_T2]; /* stage 2, includes the audio gain                  */
-    float apow[16];       /* a^(i+1), i = 0..11, a = 1 - alpha                 */
+    float apow[32];       /* a^(i+1), i = 0..OPT-1, a = 1 - alpha              */
     float alpha;
-    float a12;            /* a^12                                              */
-    float a12pow[5];      /* (a^12)^(2^s), s = 0..4                            */
-    float a384;           /* (a^12)^32                                         */
+    float a12;            /* a^OPT: decay over one thread's chunk              */
+    float a12pow[5];      /* (a^OPT)^(2^s), s = 0..4                           */
+    float a384;           /* (a^OPT)^32: decay over one warp                   */
 };
 
 struct FmParams {
@@ -123,45 +132,47 @@ struct FmParams {
     uint32_t *n_audio_out;   /* optional [capture]: number of audio samples written (streaming)        */
 };
 
-/* one input sample scattered into its (up to) 8 outputs; J is the sample index in the chunk */
+/* The scatter FIR runs as a LOOP over blocks of 40 samples (5 x 16 bytes): the taps a sample meets repeat every
+ * 10 samples with the output index moved on by one, so one block body serves the whole chunk (6.5 KB of code instead
+ * of 32 KB unrolled -- the SM's 32 KB instruction cache is shared by every resident warp, and the unrolled form
+ * stalled on instruction fetch more than on anything else, profiles/r2_wbfm.txt).
+ * J = sample index in the block; local output i (centre 10 i) takes sample J through tap k = 10 i - J and lives in
+ * acc[i & 7]; the outputs completing in the block (J = 0, 10, 20, 30) come out in out[0..3] and their slots restart
+ * as local outputs 8..11.  Between blocks the caller swaps the two halves of acc[] (local outputs 4..11 become 0..7). */
+#define B200_FM_BLK 40
 template <int J>
-B200_DEV void b200_fm_scatter(c2 x, c2 acc0, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
+B200_DEV void b200_fm_scatter(c2 x, c2 acc0, const float (&h)[40], c2 (&acc)[8], c2 (&out)[4])
 {
 #pragma unroll
     for (int i = (J + 9) / 10; i <= (J + 79) / 10; ++i) {
         const int k = 10 * i - J;
         acc[i & 7] = c2_fma_s(x, h[k < 40 ? k : 79 - k], acc[i & 7]);
     }
-    if (J % 10 == 0 && J / 10 < B200_FM_OPT) {
-#if B200_FIR_RAWU8
-        /* outputs 8..11 lived in this thread only: they hold one half of the offset, add the other */
-        head[J / 10] = (J / 10 >= 8) ? c2_add(acc[(J / 10) & 7], acc0) : acc[(J / 10) & 7];
-#else
-        head[J / 10] = acc[(J / 10) & 7];
-#endif
-        acc[(J / 10) & 7] = acc0; /* output J/10 + 8 starts here: zero, or half of the -127.5 offset */
+    if (J % 10 == 0) {
+        out[J / 10] = acc[(J / 10) & 7];
+        acc[(J / 10) & 7] = acc0; /* local output J/10 + 8 starts here: zero, or half of the -127.5 offset */
     }
 }
 
 template <int Q>
 struct b200_fm_words {
-    B200_DEVM static void run(const uint4 *raw, cvt_k cb, c2 acc0, const float (&h)[40], c2 (&acc)[8], c2 (&head)[B200_FM_OPT])
+    B200_DEVM static void run(const uint4 *raw, cvt_k cb, c2 acc0, const float (&h)[40], c2 (&acc)[8], c2 (&out)[4])
     {
         const uint4 r = raw[Q];
-        b200_fm_scatter<8 * Q + 0>(B200_FIR_X_LO(r.x, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 1>(B200_FIR_X_HI(r.x, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 2>(B200_FIR_X_LO(r.y, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 3>(B200_FIR_X_HI(r.y, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 4>(B200_FIR_X_LO(r.z, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 5>(B200_FIR_X_HI(r.z, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 6>(B200_FIR_X_LO(r.w, cb), acc0, h, acc, head);
-        b200_fm_scatter<8 * Q + 7>(B200_FIR_X_HI(r.w, cb), acc0, h, acc, head);
-        b200_fm_words<Q + 1>::run(raw, cb, acc0, h, acc, head);
+        b200_fm_scatter<8 * Q + 0>(B200_FIR_X_LO(r.x, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 1>(B200_FIR_X_HI(r.x, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 2>(B200_FIR_X_LO(r.y, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 3>(B200_FIR_X_HI(r.y, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 4>(B200_FIR_X_LO(r.z, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 5>(B200_FIR_X_HI(r.z, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 6>(B200_FIR_X_LO(r.w, cb), acc0, h, acc, out);
+        b200_fm_scatter<8 * Q + 7>(B200_FIR_X_HI(r.w, cb), acc0, h, acc, out);
+        b200_fm_words<Q + 1>::run(raw, cb, acc0, h, acc, out);
     }
 };
 template <>
-struct b200_fm_words<B200_FM_CHUNK / 8> {
-    B200_DEVM static void run(const uint4 *, cvt_k, c2, const float (&)[40], c2 (&)[8], c2 (&)[B200_FM_OPT]) {}
+struct b200_fm_words<B200_FM_BLK / 8> {
+    B200_DEVM static void run(const uint4 *, cvt_k, c2, const float (&)[40], c2 (&)[8], c2 (&)[4]) {}
 };
 
 #ifdef B200_EMULATED
@@ -203,7 +214,7 @@ B200_DEV float b200_atan2(float y, float x)
     return copysignf(r, y);
 }
 
-__global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
+__global__ void __launch_bounds__(B200_FM_THREADS, B200_FM_MINB) k_wbfm(FmParams p)
 {
     const FmTaps *taps = &c_fm_taps;
     B200_DYN_SMEM(smem);
@@ -242,11 +253,11 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
 #endif
     const float alpha = taps->alpha;
     const float a1 = 1.0f - alpha;
-    float lane_pow = 1.0f; /* (a^12)^lane */
+    float lane_pow = 1.0f; /* (a^OPT)^lane */
     for (int i = 0; i < lane; ++i) lane_pow *= taps->a12;
 
     /* carried state: segment 0 continues the stream exactly; later segments start from zero one tile
-     * early (FIR memory is 80 samples, the de-emphasis pole decays to 1e-37 over a tile) */
+     * early (FIR memory is 80 samples, the de-emphasis pole decays to nothing over a tile) */
     const FmState *st_in = (p.state && seg == 0) ? p.state + capture : nullptr;
     if (tid < 8) {
         float tr = 0.0f, ti = 0.0f;
@@ -263,8 +274,8 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         s_ylastc[1] = c2_make(yr, yi);
     }
     if (tid == 9) s_wsum[4] = st_in ? st_in->e_last : 0.0f; /* tile carry e[m0-1] */
-    if (tid >= 32 && tid < 32 + B200_FM_HIST)
-        s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32] = st_in ? st_in->e_hist[tid - 32] : 0.0f;
+    for (int i = tid; i < B200_FM_HIST; i += B200_FM_THREADS)
+        s_e[B200_FM_HPAD - B200_FM_HIST + i] = st_in ? st_in->e_hist[i] : 0.0f;
 
     auto issue_tile = [&](uint32_t it) { /* thread 0 only */
         const uint32_t tile = t_begin + it;
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         if (last > B200_FM_THREADS - 1) last = B200_FM_THREADS - 1;
         const int par = (int)(it & 1);
 
-        /* ---- stage 1: scatter FIR over this thread's 120 samples ---- */
+        /* ---- stage 1: scatter FIR over this thread's 200 samples ---- */
         b200_mbar_wait(s_bar, it & 1);
         c2 acc[8], head[B200_FM_OPT];
         /* the very first chunk of a capture / stream: its outputs 0..7 are the filter's rise from nothing
@@ -302,16 +313,42 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
         const c2 start = (tid == 0 && it == 0 && seg == 0 && p.m_base == 0) ? c2_zero() : acc0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = start;
-        const uint4 *raw = reinterpret_cast<const uint4 *>(smem + B200_FM_SM_RAW + tid * (2 * B200_FM_CHUNK));
-        b200_fm_words<0>::run(raw, cb, acc0, h, acc, head);
-        /* tails: outputs 12..19 live in acc[i & 7] -> next thread's heads 0..7.
+        unsigned char *my_raw = smem + B200_FM_SM_RAW + tid * (2 * B200_FM_CHUNK);
+        /* the 4 outputs a block completes are parked in the part of this thread's OWN raw bytes it has already
+         * consumed (32 bytes of results per 80 bytes of input; no other thread ever reads these bytes) and come
+         * back into registers after the FIR: that keeps the block body free of chunk-position-dependent code */
+        c2 *park = reinterpret_cast<c2 *>(my_raw);
+#pragma unroll 1
+        for (int blk = 0; blk < B200_FM_CHUNK / B200_FM_BLK; ++blk) {
+            c2 out[4];
+            b200_fm_words<0>::run(reinterpret_cast<const uint4 *>(my_raw) + blk * (B200_FM_BLK / 8), cb, acc0, h, acc, out);
+#if B200_FIR_RAWU8
+            /* outputs 8.. of the chunk (blocks 2..) lived in this thread only: they hold one half of the offset, add
+             * the other; outputs 0..7 get theirs from the previous thread's tails */
+            const c2 fix = blk >= 2 ? acc0 : c2_zero();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = c2_add(out[q], fix);
+#endif
+#pragma unroll
+            for (int q = 0; q < 4; ++q) park[4 * blk + q] = out[q];
+            /* local outputs 4..11 of this block are 0..7 of the next */
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const c2 t = acc[q];
+                acc[q] = acc[q + 4];
+                acc[q + 4] = t;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B200_FM_OPT; ++i) head[i] = park[i];
+        /* tails: outputs OPT..OPT+7 are acc[0..7] after the last swap -> next thread's heads 0..7.
          * exchange tile is [i][thread] so a warp's stores / loads are contiguous */
         if (tid == last) {
 #pragma unroll
-            for (int i = 12; i < 20; ++i) s_tailc[par * 8 + (i - 12)] = acc[i & 7];
+            for (int i = 0; i < 8; ++i) s_tailc[par * 8 + i] = acc[i];
         } else {
 #pragma unroll
-            for (int i = 12; i < 20; ++i) s_tail[(i - 12) * B200_FM_TAILP + tid + 1] = acc[i & 7];
+            for (int i = 0; i < 8; ++i) s_tail[i * B200_FM_TAILP + tid + 1] = acc[i];
         }
         __syncthreads(); /* S1: raw buffer consumed, tails visible */
         if (tid == 0 && it + 1 < my_tiles) issue_tile(it + 1);
@@ -358,7 +395,7 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
                 e[i] = run;
             }
         }
-        /* warp scan of the chunk totals: v_l = sum_{l'<=l} (a^12)^(l-l') E11_l' */
+        /* warp scan of the chunk totals: v_l = sum_{l'<=l} (a^OPT)^(l-l') E_l' */
         float v = e[B200_FM_OPT - 1];
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
@@ -376,46 +413,65 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
 #pragma unroll
             for (int i = 0; i < B200_FM_OPT; ++i) e[i] = fmaf(taps->apow[i], cin, e[i]);
             float4 *dst = reinterpret_cast<float4 *>(s_e + B200_FM_HPAD + tid * B200_FM_OPT);
-            dst[0] = make_float4(e[0], e[1], e[2], e[3]);
-            dst[1] = make_float4(e[4], e[5], e[6], e[7]);
-            dst[2] = make_float4(e[8], e[9], e[10], e[11]);
+#pragma unroll
+            for (int q = 0; q < B200_FM_OPT / 4; ++q) dst[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
         }
         __syncthreads(); /* S4 */
 
-        /* ---- stage 2: audio[p] = sum_k h2[k] e[5 p - k]; a thread takes 3 consecutive p and reads
-         * its 60-sample window of e[] once ---- */
+        /* ---- stage 2: audio[p] = sum_k h2[k] e[5 p - k].  A tile starts at a multiple of 20 stage-1 outputs
+         * (chunks are whole), so thread t owns exactly the four audio samples p = pg_first + 4 t + r whose
+         * newest input is its own e[5 r]: the 65-float window e[20 t - 49 .. 20 t + 15] sits at the FIXED
+         * offset 3 behind the 16-byte aligned address s_e + 20 t (HPAD - HIST = 3) and is read with 17
+         * 128-bit loads; the taps run outermost, so each is fetched once for the four outputs ---- */
         {
-            const uint64_t mg0 = p.m_base + m0; /* global stage-1 index of tile start */
+            const uint64_t mg0 = p.m_base + m0; /* global stage-1 index of tile start: a multiple of 20 */
             uint64_t mg_end = mg0 + (uint64_t)(last + 1) * B200_FM_OPT;
             if (mg_end > p.m_base + p.m1) mg_end = p.m_base + p.m1;
-            const uint64_t pg_first = (mg0 + B200_FM_D2 - 1) / B200_FM_D2;
+            const uint64_t pg_first = mg0 / B200_FM_D2;
             const uint64_t pg_end = (mg_end + B200_FM_D2 - 1) / B200_FM_D2;
             const uint64_t pg0 = pg_first + (uint64_t)tid * B200_FM_APT;
             if (pg0 < pg_end) {
-                const float *win = s_e + B200_FM_HPAD + (int)(pg0 * B200_FM_D2 - mg0) - B200_FM_HIST;
-                float ew[B200_FM_T2 + B200_FM_D2 * (B200_FM_APT - 1)];
+                constexpr int WOFF = B200_FM_HPAD - B200_FM_HIST; /* 3 */
+                constexpr int NW4 = (WOFF + B200_FM_T2 + B200_FM_D2 * (B200_FM_APT - 1) + 3) / 4; /* 17 */
+                const float4 *win = reinterpret_cast<const float4 *>(s_e + tid * B200_FM_OPT);
+                float ew[4 * NW4];
 #pragma unroll
-                for (int j = 0; j < B200_FM_T2 + B200_FM_D2 * (B200_FM_APT - 1); ++j) ew[j] = win[j];
+                for (int j = 0; j < NW4; ++j) {
+                    const float4 q = win[j];
+                    ew[4 * j] = q.x; ew[4 * j + 1] = q.y; ew[4 * j + 2] = q.z; ew[4 * j + 3] = q.w;
+                }
+                float au[B200_FM_APT];
 #pragma unroll
-                for (int r = 0; r < B200_FM_APT; ++r) {
-                    float s0 = 0.0f, s1 = 0.0f;
+                for (int r = 0; r < B200_FM_APT; ++r) au[r] = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < B200_FM_T2; k += 2) {
-                        s0 = fmaf(taps->h2[k], ew[B200_FM_HIST + B200_FM_D2 * r - k], s0);
-                        s1 = fmaf(taps->h2[k + 1], ew[B200_FM_HIST + B200_FM_D2 * r - k - 1], s1);
-                    }
-                    if (store && pg0 + r < pg_end)
-                        p.audio[(uint64_t)capture * p.audio_stride + (pg0 + r - p.audio_base)] = s0 + s1;
+                for (int k = 0; k < B200_FM_T2; ++k) {
+                    const float hk = taps->h2[k];
+#pragma unroll
+                    for (int r = 0; r < B200_FM_APT; ++r) au[r] = fmaf(hk, ew[WOFF + B200_FM_HIST + B200_FM_D2 * r - k], au[r]);
+                }
+                if (store) {
+                    float *dst = p.audio + (uint64_t)capture * p.audio_stride + (pg0 - p.audio_base);
+#pragma unroll
+                    for (int r = 0; r < B200_FM_APT; ++r)
+                        if (pg0 + r < pg_end) dst[r] = au[r];
                 }
             }
         }
         __syncthreads(); /* S5 */
         /* e carries for the next tile (tails / ylast travel through the parity buffers) */
         if (tid == 9) s_wsum[4] = s_e[B200_FM_HPAD + (last + 1) * B200_FM_OPT - 1];
-        float hv = 0.0f;
-        if (tid >= 32 && tid < 32 + B200_FM_HIST) hv = s_e[B200_FM_HPAD + (last + 1) * B200_FM_OPT - B200_FM_HIST + tid - 32];
+        float hv[(B200_FM_HIST + B200_FM_THREADS - 1) / B200_FM_THREADS];
+#pragma unroll
+        for (int q = 0; q < (B200_FM_HIST + B200_FM_THREADS - 1) / B200_FM_THREADS; ++q) {
+            const int i = tid + q * B200_FM_THREADS;
+            hv[q] = i < B200_FM_HIST ? s_e[B200_FM_HPAD + (last + 1) * B200_FM_OPT - B200_FM_HIST + i] : 0.0f;
+        }
         __syncthreads(); /* S6: history source read before it is overwritten (partial tiles overlap) */
-        if (tid >= 32 && tid < 32 + B200_FM_HIST) s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32] = hv;
+#pragma unroll
+        for (int q = 0; q < (B200_FM_HIST + B200_FM_THREADS - 1) / B200_FM_THREADS; ++q) {
+            const int i = tid + q * B200_FM_THREADS;
+            if (i < B200_FM_HIST) s_e[B200_FM_HPAD - B200_FM_HIST + i] = hv[q];
+        }
         /* the next tile's S1..S3 order these writes before their readers */
     }
 
@@ -436,8 +492,8 @@ __global__ void __launch_bounds__(B200_FM_THREADS, 4) k_wbfm(FmParams p)
             st_out->ylast[1] = yi;
         }
         if (tid == 9) st_out->e_last = s_wsum[4];
-        if (tid >= 32 && tid < 32 + B200_FM_HIST)
-            st_out->e_hist[tid - 32] = s_e[B200_FM_HPAD - B200_FM_HIST + tid - 32];
+        for (int i = tid; i < B200_FM_HIST; i += B200_FM_THREADS)
+            st_out->e_hist[i] = s_e[B200_FM_HPAD - B200_FM_HIST + i];
     }
 }
 

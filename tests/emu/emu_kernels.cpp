@@ -114,6 +114,7 @@ int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, v
 }
 
 int emu_sizeof_fm_state(void) { return (int)sizeof(FmState); }
+int emu_fm_chunk(void) { return B200_FM_CHUNK; }
 
 /* the product's spectrum launch plan (csrc/plan.h): out4 = frames, frames_per_warp, units_per_capture, grid */
 void emu_plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count, uint32_t *out4)

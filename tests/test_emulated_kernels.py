@@ -202,7 +202,9 @@ def test_wbfm_streaming_state_carry(emu, g, tps):
     """tps = tiles per segment of every streaming launch (0: one CTA walks the whole block; otherwise
     the block is split over CTAs: segment 0 continues the carried state, the others pre-roll a tile)"""
     nch = 700
-    n = 120 * nch
+    ch = emu.emu_fm_chunk()                     # input samples per thread-chunk (csrc/wbfm.cuh B200_FM_CHUNK)
+    opt = ch // 10
+    n = ch * nch
     iq = padded(g.synth(1, 2 * n, SYNTH_WBFM, 3))
     ga, gd = g.wbfm(iq[: 2 * n], want_disc=True)
     state = np.zeros(emu.emu_sizeof_fm_state(), np.uint8)
@@ -212,10 +214,10 @@ def test_wbfm_streaming_state_carry(emu, g, tps):
     while pos < nch:
         k = small.pop(0) if small else int(min(nch - pos, rng.integers(1, 300)))
         k = int(min(k, nch - pos))
-        a = np.zeros(k * 12 // 5 + 2, np.float32)
-        d = np.zeros(k * 12, np.float32)
+        a = np.zeros(k * opt // 5 + 2, np.float32)
+        d = np.zeros(k * opt, np.float32)
         na = C.c_uint32(0)
-        emu.emu_wbfm_stream(iq[pos * 240:].ctypes.data, k, pos, state.ctypes.data, a.ctypes.data, C.byref(na), d.ctypes.data, tps)
+        emu.emu_wbfm_stream(iq[pos * 2 * ch:].ctypes.data, k, pos, state.ctypes.data, a.ctypes.data, C.byref(na), d.ctypes.data, tps)
         outa.append(a[: na.value])
         outd.append(d)
         pos += k

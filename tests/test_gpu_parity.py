@@ -331,7 +331,7 @@ def test_streaming_all_chains_block_cut_invariance(sdr_lib, g, cuts_kind, submit
     spec_check(spec, gold_spec)
     # audio produced so far = every output whose chunk is complete
     ga = g.wbfm(iq)
-    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_fm = sdr_lib.wbfm_stream_audio_len(total)
     assert fm.size == n_fm and np.max(np.abs(fm - ga[:n_fm])) <= FM_AUDIO_ATOL
     gam = g.am(iq)
     n_am = (2 * (total // 2 // 200) + 2) // 3
@@ -456,7 +456,7 @@ def test_audio_fifo_partial_pops_and_back_pressure(sdr_lib, g):
                 break
     fm, am = np.concatenate(got_fm), np.concatenate(got_am)
     assert busy > 0
-    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_fm = sdr_lib.wbfm_stream_audio_len(total)
     n_am = (2 * (total // 2 // 200) + 2) // 3
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
     assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
@@ -604,7 +604,7 @@ def test_streaming_tiny_blocks(sdr_lib, g, submit_bytes):
     gold, gframes = g.spectrum(iq)
     assert frames == gframes == 4
     spec_check_few_frames(spec, gold)
-    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_fm = sdr_lib.wbfm_stream_audio_len(total)
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
 
 
@@ -632,7 +632,7 @@ def test_streaming_wraps_the_device_stream_buffer_many_times(sdr_lib, g, submit_
     gold, gframes = g.spectrum(iq)
     assert frames == gframes
     spec_check(spec, gold)
-    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_fm = sdr_lib.wbfm_stream_audio_len(total)
     n_am = (2 * (total // 2 // 200) + 2) // 3
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
     assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
@@ -652,7 +652,7 @@ def test_example_host_driver_runs(sdr_lib, g, tmp_path):
     iq = g.synth(1, total, SYNTH_WBFM, 0)
     fm = np.fromfile(tmp_path / "fm48k.f32", np.float32)
     am = np.fromfile(tmp_path / "am8k.f32", np.float32)
-    n_fm = -(-((total // 2 // 120) * 12) // 5)
+    n_fm = sdr_lib.wbfm_stream_audio_len(total)
     n_am = (2 * (total // 2 // 200) + 2) // 3
     assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
     assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
@@ -691,7 +691,7 @@ def test_contexts_are_independent(sdr_lib, g):
             assert frames == gframes
             spec_check(spec, gold)
             fm, am = s.get_audio(sdr_lib.CHAIN_WBFM), s.get_audio(sdr_lib.CHAIN_AM)
-            n_fm = -(-((total // 2 // 120) * 12) // 5)
+            n_fm = sdr_lib.wbfm_stream_audio_len(total)
             n_am = (2 * (total // 2 // 200) + 2) // 3
             assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
             assert am.size == n_am and np.max(np.abs(am - g.am(iq)[:n_am])) <= AM_AUDIO_ATOL
@@ -780,6 +780,6 @@ def test_one_big_slot_fits_a_small_audio_fifo(sdr_lib, g):
     with sdr_lib.B200Sdr(slot_bytes=blk, ring_slots=2, audio_capacity=4096) as s:
         assert s.process_samples(iq, allow_busy=True) == sdr_lib.OK
         fm = s.get_audio(sdr_lib.CHAIN_WBFM)
-        n_fm = -(-((blk // 2 // 120) * 12) // 5)
+        n_fm = sdr_lib.wbfm_stream_audio_len(blk)
         assert fm.size == n_fm and np.max(np.abs(fm - g.wbfm(iq)[:n_fm])) <= FM_AUDIO_ATOL
         assert s.process_samples(iq, allow_busy=True) == sdr_lib.OK     # and again after the pop
