@@ -575,9 +575,23 @@ def main():
         s2.close()
         # the firmware's own cadence from a plain C caller (examples/firmware_cadence.c): ONE 512-byte
         # buffer re-armed after every process_samples() call, spectrum read back every 4096 blocks
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+        # the same from a plain C caller (examples/ingest_bench.c), 256 KiB slots: process_samples (the block is copied into
+        # the pinned slot) and ring_acquire / ring_commit (zero-copy: the producer fills the slot, only the enqueue is timed)
+        ib = os.path.join(ROOT, "build", "ingest_bench")
+        if os.path.exists(ib):
+            try:
+                out = subprocess.run([ib, str(blk), "2048"], capture_output=True, text=True, timeout=120, env=env).stdout
+                for ln in out.splitlines():
+                    if ln.startswith("INGEST"):
+                        kv = dict(t.split("=") for t in ln.split()[1:])
+                        ingest["c_caller_" + kv["mode"]] = {"us_per_block": float(kv["us_per_block"]), "GBps": float(kv["GBps"]),
+                                                            "MSps": float(kv["MSps"]), "busy_returns": int(kv["busy"]),
+                                                            "realtime_factor_at_2.4MSps": float(kv["realtime"])}
+            except Exception as e:  # the probe is informative only
+                ingest["c_caller"] = {"error": str(e)[:200]}
         fw = os.path.join(ROOT, "build", "firmware_cadence")
         if os.path.exists(fw):
-            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
             for key, argv in (("firmware_512B_coalesced", ["96000000", "512", "0", "262144", "4096"]),
                               ("firmware_512B_per_block", ["2048000", "512", "4", "262144", "4096"])):
                 try:

@@ -57,6 +57,13 @@ struct b200sdr_ctx {
     b200sdr_config cfg{};
     int device = 0, sm_count = 148;
     cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    /* streaming path: one stream per chain (0 spectrum, 1 WBFM, 2 AM, 3 counter).  The chains of a ring slot share
+     * nothing but their input bytes, so they run side by side behind the slot's H2D copy; a slot then costs the device
+     * the SLOWEST chain instead of their sum (small launches are latency-, not throughput-bound) */
+    cudaStream_t s_chain[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chain[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *d_partials_stream = nullptr; size_t partials_stream_floats = 0; /* streaming k_spectrum's own workspace ...  */
+    uint32_t *d_unit_counter_stream = nullptr;                             /* ... and hand-out counter (it may run next to a batch launch) */
     bool failed = false;     /* sticky: a chain failed after its H2D was enqueued (see commit_slot) */
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     uint64_t launches = 0;
@@ -160,13 +167,21 @@ int ensure_floats(b200sdr_ctx *ctx, float **p, size_t *have, size_t want)
 /* ---- launches --------------------------------------------------------------------------- */
 int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t stride, uint64_t len_bytes,
                     bool ema, const float *carry, float carry_scale, float scale_override, bool use_scale_override,
-                    float *out_dev, bool finalize = true)
+                    float *out_dev, bool finalize = true, bool streaming = false)
 {
     b200::SpectrumPlan pl = b200::plan_spectrum(len_bytes, n_captures, (uint32_t)ctx->sm_count);
     if (pl.frames == 0) return B200SDR_OK;
     if (pl.total_units > 0xffffffffull) return fail(ctx, B200SDR_NOT_SUPPORTED, "batch too large (32-bit work-unit index)");
-    int rc = ensure_floats(ctx, &ctx->d_partials, &ctx->partials_floats, (size_t)pl.total_units * 1024);
+    cudaStream_t stream = streaming ? ctx->s_chain[0] : ctx->s_compute;
+    float **partials = streaming ? &ctx->d_partials_stream : &ctx->d_partials;
+    size_t *partials_cap = streaming ? &ctx->partials_stream_floats : &ctx->partials_floats;
+    if (*partials_cap < (size_t)pl.total_units * 1024 && *partials) CU(cudaStreamSynchronize(stream));
+    int rc = ensure_floats(ctx, partials, partials_cap, (size_t)pl.total_units * 1024);
     if (rc) return rc;
+    float scale = ema ? 1.0f : 1.0f / (float)pl.frames;
+    if (use_scale_override) scale = scale_override;
+    /* short single captures (ring slots): the last CTA finalizes, one launch less */
+    const bool fold = finalize && n_captures == 1 && pl.total_units <= 128;
     SpectrumParams p{};
     p.iq = iq_dev;
     p.capture_stride = stride;
@@ -174,22 +189,21 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     p.frames_per_warp = pl.frames_per_warp;
     p.window = ctx->d_window[ctx->cfg.window];
     p.twiddle = ctx->d_twiddle;
-    p.partials = ctx->d_partials;
+    p.partials = *partials;
     p.units_per_capture = pl.units_per_capture;
     p.total_units = (uint32_t)pl.total_units;
-    p.unit_counter = ctx->d_unit_counter;
+    p.unit_counter = streaming ? ctx->d_unit_counter_stream : ctx->d_unit_counter;
     p.ema_beta = ctx->cfg.ema_beta;
     p.ema_log2_decay = log2f(1.0f - ctx->cfg.ema_beta);
+    if (fold) { p.final_out = out_dev; p.carry = carry; p.carry_scale = carry_scale; p.final_scale = scale; }
     dim3 grid(pl.grid);
-    if (ema) k_spectrum<true><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
-    else k_spectrum<false><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, ctx->s_compute>>>(p);
+    if (ema) k_spectrum<true><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, stream>>>(p);
+    else k_spectrum<false><<<grid, B200_SPEC_THREADS, B200_SPEC_SMEM_BYTES, stream>>>(p);
     CU(cudaGetLastError());
     ctx->launches += 1;
-    if (!finalize) return B200SDR_OK; /* the caller reduces ctx->d_partials itself (split-capture exchange) */
-    float scale = ema ? 1.0f : 1.0f / (float)pl.frames;
-    if (use_scale_override) scale = scale_override;
-    k_spectrum_finalize<<<dim3(4, n_captures), 256, 0, ctx->s_compute>>>(ctx->d_partials, pl.units_per_capture, scale,
-                                                                         carry, carry_scale, out_dev);
+    if (!finalize || fold) return B200SDR_OK; /* !finalize: the caller reduces ctx->d_partials itself (split-capture exchange) */
+    k_spectrum_finalize<<<dim3(4, n_captures), 256, 0, stream>>>(*partials, pl.units_per_capture, scale,
+                                                                 carry, carry_scale, out_dev);
     CU(cudaGetLastError());
     ctx->launches += 1;
     return B200SDR_OK;
@@ -249,7 +263,8 @@ int launch_am_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
 }
 
 bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
-int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where);
+int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where, cudaStream_t stream);
+int join_chains(b200sdr_ctx *ctx);
 
 /* ---- streaming steps: all on the compute stream, after the new bytes are in d_stream[.. wpos) ---- */
 int stream_spectrum(b200sdr_ctx *ctx)
@@ -261,7 +276,7 @@ int stream_spectrum(b200sdr_ctx *ctx)
     /* mean: acc += sum |X|^2 ; EMA: acc = (1-beta)^F acc + sum beta (1-beta)^(F-1-m) |X_m|^2 */
     const float carry_scale = ema ? powf(1.0f - ctx->cfg.ema_beta, (float)frames) : 1.0f;
     int rc = launch_spectrum(ctx, ctx->d_stream + ctx->spec_off, 1, 0, have, ema, ctx->d_spec_acc, carry_scale, 1.0f, true,
-                             ctx->d_spec_acc);
+                             ctx->d_spec_acc, true, true);
     if (rc) return rc;
     ctx->spec_frames += frames;
     ctx->spec_off += frames * 1024u; /* 512 samples x 2 bytes per frame; the 512-sample overlap stays unread */
@@ -285,13 +300,13 @@ int stream_wbfm(b200sdr_ctx *ctx)
     const uint32_t segments = (uint32_t)b200::ceil_div(p.n_tiles, p.tiles_per_segment);
     const uint64_t a0 = b200::ceil_div(p.m_base, B200_FM_D2), a1 = b200::ceil_div(p.m_base + p.m1, B200_FM_D2);
     const uint32_t n_audio = (uint32_t)(a1 - a0);
-    int frc = fifo_reserve(ctx, ctx->fm_fifo, n_audio, &p.audio);
+    int frc = fifo_reserve(ctx, ctx->fm_fifo, n_audio, &p.audio, ctx->s_chain[1]);
     if (frc) return frc;
     p.audio_base = a0;
     p.state = ctx->d_fm_state + ctx->fm_state_cur;
     p.state_out = ctx->d_fm_state + (ctx->fm_state_cur ^ 1);
     ctx->fm_state_cur ^= 1;
-    k_wbfm<<<dim3(segments, 1), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_compute>>>(p);
+    k_wbfm<<<dim3(segments, 1), B200_FM_THREADS, B200_FM_SMEM_BYTES, ctx->s_chain[1]>>>(p);
     CU(cudaGetLastError());
     ctx->launches += 1;
     ctx->fm_fifo.count += n_audio;
@@ -308,7 +323,7 @@ int stream_am(b200sdr_ctx *ctx)
     const uint64_t a0 = (2 * ctx->am_chunks + 2) / 3, a1 = (2 * (ctx->am_chunks + n_chunks) + 2) / 3;
     const uint32_t n_audio = (uint32_t)(a1 - a0);
     float *am_out = nullptr;
-    int frc = fifo_reserve(ctx, ctx->am_fifo, n_audio, &am_out);
+    int frc = fifo_reserve(ctx, ctx->am_fifo, n_audio, &am_out, ctx->s_chain[2]);
     if (frc) return frc;
     AmFrontParams p{};
     p.iq = ctx->d_stream + ctx->am_off;
@@ -323,7 +338,7 @@ int stream_am(b200sdr_ctx *ctx)
     p.state = ctx->d_amf_state + ctx->amf_state_cur;
     p.state_out = ctx->d_amf_state + (ctx->amf_state_cur ^ 1);
     ctx->amf_state_cur ^= 1;
-    k_am_front<<<dim3(segments, 1), B200_AM_THREADS, B200_AM_SMEM_BYTES, ctx->s_compute>>>(p);
+    k_am_front<<<dim3(segments, 1), B200_AM_THREADS, B200_AM_SMEM_BYTES, ctx->s_chain[2]>>>(p);
     CU(cudaGetLastError());
     AmBackParams b{};
     b.env = ctx->d_am_env_stream;
@@ -332,7 +347,7 @@ int stream_am(b200sdr_ctx *ctx)
     b.audio = am_out;
     b.audio_base = a0;
     b.state = ctx->d_amb_state;
-    k_am_back<<<1, B200_AMB_THREADS, 0, ctx->s_compute>>>(b);
+    k_am_back<<<1, B200_AMB_THREADS, 0, ctx->s_chain[2]>>>(b);
     CU(cudaGetLastError());
     ctx->launches += 2;
     ctx->am_fifo.count += n_audio;
@@ -351,7 +366,7 @@ int stream_counter(b200sdr_ctx *ctx, uint32_t len)
     p.expect_first = -1;
     p.stream = ctx->d_cnt_state;
     p.pos_base = ctx->cnt_bytes;
-    k_counter_check<<<dim3((unsigned)b200::ceil_div(b200::ceil_div(p.n_words, 4), 1024), 1), 256, 0, ctx->s_compute>>>(p);
+    k_counter_check<<<dim3((unsigned)b200::ceil_div(b200::ceil_div(p.n_words, 4), 1024), 1), 256, 0, ctx->s_chain[3]>>>(p);
     CU(cudaGetLastError());
     ctx->launches += 1;
     ctx->cnt_bytes += len;
@@ -378,7 +393,10 @@ int reset_stream_state(b200sdr_ctx *ctx)
     CU(cudaMemsetAsync(ctx->d_amf_state, 0, 2 * sizeof(AmFrontState), ctx->s_compute));
     ctx->amf_state_cur = 0;
     CU(cudaMemsetAsync(ctx->d_amb_state, 0, sizeof(AmBackState), ctx->s_compute));
-    return reset_counter_state(ctx);
+    int rc = reset_counter_state(ctx);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->s_compute)); /* the chain streams start from the cleared state */
+    return B200SDR_OK;
 }
 
 const float *synth_lut_host()
@@ -407,8 +425,10 @@ int wrap_stream(b200sdr_ctx *ctx)
     if ((ctx->cfg.chains & B200SDR_CHAIN_AM) && ctx->am_off < lo) lo = ctx->am_off;
     const uint64_t shift = lo & ~(uint64_t)15, tail = ctx->wpos - shift;
     if (shift < tail) return fail(ctx, B200SDR_FAIL, "stream buffer too small for the unread tail");
-    /* on the compute stream the move is ordered after every kernel that read the old data; the H2D copies
-     * that follow (copy stream) wait for it */
+    /* on the compute stream, behind every chain kernel that read the old data; the H2D copies that follow (copy
+     * stream, and through its per-slot events the chain streams) wait for the move */
+    int jrc = join_chains(ctx);
+    if (jrc) return jrc;
     if (tail) CU(cudaMemcpyAsync(ctx->d_stream, ctx->d_stream + shift, tail, cudaMemcpyDeviceToDevice, ctx->s_compute));
     CU(cudaEventRecord(ctx->ev_wrapped, ctx->s_compute));
     CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_wrapped, 0));
@@ -437,7 +457,9 @@ int commit_slot(b200sdr_ctx *ctx, uint32_t slot, uint32_t len)
     ctx->wpos += len;
     int rc = B200SDR_OK;
     cudaError_t e = cudaEventRecord(ctx->ev_copied[slot], ctx->s_copy);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[slot], 0);
+    static const uint32_t chain_bit[4] = {B200SDR_CHAIN_SPECTRUM, B200SDR_CHAIN_WBFM, B200SDR_CHAIN_AM, B200SDR_CHAIN_COUNTER};
+    for (int c = 0; c < 4 && e == cudaSuccess; ++c)
+        if (ctx->cfg.chains & chain_bit[c]) e = cudaStreamWaitEvent(ctx->s_chain[c], ctx->ev_copied[slot], 0);
     if (e != cudaSuccess) rc = fail(ctx, B200SDR_FAIL, "ring slot hand-over", e);
     if (!rc && (ctx->cfg.chains & B200SDR_CHAIN_SPECTRUM)) rc = stream_spectrum(ctx);
     if (!rc && (ctx->cfg.chains & B200SDR_CHAIN_WBFM)) rc = stream_wbfm(ctx);
@@ -492,11 +514,22 @@ int upload_thresholds(b200sdr_ctx *ctx, float db_min, float db_max)
 }
 
 /* contiguous room for n more floats behind the queued ones (compacting if the tail is used up) */
-int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where)
+/* every chain stream -> the compute stream: after this, whatever is enqueued on (or synchronised through) s_compute
+ * comes after all streaming kernels submitted so far */
+int join_chains(b200sdr_ctx *ctx)
+{
+    for (int c = 0; c < 4; ++c) {
+        CU(cudaEventRecord(ctx->ev_chain[c], ctx->s_chain[c]));
+        CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_chain[c], 0));
+    }
+    return B200SDR_OK;
+}
+
+int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where, cudaStream_t stream)
 {
     if (f.count + n > f.capacity) return fail(ctx, B200SDR_FAIL, "audio FIFO overflow");
     if (f.head + f.count + n > f.capacity) {
-        CU(cudaMemcpyAsync(f.d_spare, f.d_buf + f.head, (size_t)f.count * sizeof(float), cudaMemcpyDeviceToDevice, ctx->s_compute));
+        CU(cudaMemcpyAsync(f.d_spare, f.d_buf + f.head, (size_t)f.count * sizeof(float), cudaMemcpyDeviceToDevice, stream));
         float *t = f.d_buf; f.d_buf = f.d_spare; f.d_spare = t;
         f.head = 0;
     }
@@ -506,6 +539,8 @@ int fifo_reserve(b200sdr_ctx *ctx, AudioFifo &f, uint32_t n, float **where)
 
 int pop_fifo(b200sdr_ctx *ctx, AudioFifo &f, float *out, uint32_t capacity, uint32_t *n_out)
 {
+    int jrc = join_chains(ctx);
+    if (jrc) return jrc;
     CU(cudaStreamSynchronize(ctx->s_compute));
     const uint32_t n = f.count < capacity ? f.count : capacity;
     if (n) CU(cudaMemcpy(out, f.d_buf + f.head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -583,6 +618,10 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int c = 0; c < 4; ++c) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_chain[c], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_chain[c], cudaEventDisableTiming));
+    }
     CK(cudaEventCreate(&ctx->ev_t0));
     CK(cudaEventCreate(&ctx->ev_t1));
     for (int i = 0; i < 2; ++i) {
@@ -642,6 +681,8 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     CK(cudaMalloc((void **)&ctx->d_spec_acc, 1024 * sizeof(float)));
     CK(cudaMalloc((void **)&ctx->d_unit_counter, 2 * sizeof(uint32_t)));
     CK(cudaMemset(ctx->d_unit_counter, 0, 2 * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_unit_counter_stream, 2 * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_unit_counter_stream, 0, 2 * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_cnt_state, sizeof(CounterStreamState)));
     CK(cudaMalloc((void **)&ctx->d_fm_state, 2 * sizeof(FmState)));
     CK(cudaMalloc((void **)&ctx->d_amf_state, 2 * sizeof(AmFrontState)));
@@ -684,7 +725,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
-    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc, ctx->d_unit_counter,
+    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc, ctx->d_unit_counter, ctx->d_unit_counter_stream, ctx->d_partials_stream,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
@@ -693,6 +734,10 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int c = 0; c < 4; ++c) {
+        if (ctx->s_chain[c]) cudaStreamDestroy(ctx->s_chain[c]);
+        if (ctx->ev_chain[c]) cudaEventDestroy(ctx->ev_chain[c]);
+    }
     delete ctx;
     return B200SDR_OK;
 }
@@ -772,6 +817,8 @@ int32_t b200sdr_sync(b200sdr_ctx *ctx)
         if (rc) return rc;
     }
     CU(cudaStreamSynchronize(ctx->s_copy));
+    int jrc = join_chains(ctx);
+    if (jrc) return jrc;
     CU(cudaStreamSynchronize(ctx->s_compute));
     return B200SDR_OK;
 }
@@ -796,7 +843,7 @@ int32_t b200sdr_get_spectrum(b200sdr_ctx *ctx, float *out1024, uint64_t *n_frame
         int rc = flush_pending(ctx);
         if (rc) return rc;
     }
-    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_chain[0]));
     CU(cudaMemcpy(out1024, ctx->d_spec_acc, 1024 * sizeof(float), cudaMemcpyDeviceToHost));
     if (ctx->cfg.avg_mode == B200SDR_AVG_MEAN && ctx->spec_frames) {
         const float s = 1.0f / (float)ctx->spec_frames;
@@ -837,6 +884,8 @@ int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capaci
         if (rc) return rc;
     }
     CU(cudaStreamSynchronize(ctx->s_copy));
+    int jrc = join_chains(ctx);
+    if (jrc) return jrc;
     CU(cudaStreamSynchronize(ctx->s_compute));
     uint32_t n = ctx->last_len < capacity ? ctx->last_len : capacity;
     if (n) CU(cudaMemcpy(out, ctx->d_stream + ctx->last_pos + ctx->last_off, n, cudaMemcpyDeviceToHost));
@@ -1066,8 +1115,8 @@ int32_t b200sdr_get_counter_check(b200sdr_ctx *ctx, uint64_t *n_breaks, uint64_t
     int rc = flush_pending(ctx);
     if (rc) return rc;
     CounterStreamState st{};
-    CU(cudaMemcpyAsync(&st, ctx->d_cnt_state, sizeof st, cudaMemcpyDeviceToHost, ctx->s_compute));
-    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaMemcpyAsync(&st, ctx->d_cnt_state, sizeof st, cudaMemcpyDeviceToHost, ctx->s_chain[3]));
+    CU(cudaStreamSynchronize(ctx->s_chain[3]));
     if (n_breaks) *n_breaks = st.n_breaks;
     if (first_break) *first_break = st.first_break;
     return B200SDR_OK;
@@ -1180,6 +1229,10 @@ int32_t b200sdr_render_spectrum(b200sdr_ctx *ctx, const float *spectrum_host, fl
     if (!spectrum_host && !ctx->slot_acquired) { /* the streaming spectrum must include every accepted block */
         int frc = flush_pending(ctx);
         if (frc) return frc;
+    }
+    if (!spectrum_host) { /* the render kernel (compute stream) reads what the spectrum chain's stream wrote */
+        int jrc = join_chains(ctx);
+        if (jrc) return jrc;
     }
     const size_t img_bytes = (size_t)B200_LCD_W * B200_LCD_H * sizeof(uint32_t);
     uint32_t *d_img = nullptr;

@@ -67,8 +67,9 @@ inline SpectrumPlan plan_spectrum(uint64_t len_bytes, uint32_t n_captures, uint3
 }
 
 /* ---- WBFM ---- */
-/* streaming launches: tiles per CTA.  2 keeps the pre-roll overhead at one extra tile per two. */
-constexpr uint32_t kFmStreamTilesPerSegment = 2;
+/* streaming launches: tiles per CTA.  A ring slot is a handful of tiles and the GPU is otherwise idle, so what counts is
+ * the slot's latency: one tile per CTA (each CTA after the first also pre-rolls the tile before its own) */
+constexpr uint32_t kFmStreamTilesPerSegment = 1;
 struct FmPlan {
     uint32_t n_tiles, total_chunks, tiles_per_segment, segments;
     uint64_t m1;

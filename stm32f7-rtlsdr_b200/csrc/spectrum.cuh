@@ -109,6 +109,11 @@ struct SpectrumParams {
     uint32_t total_units;     /* n_captures x units_per_capture                                  */
     uint32_t *unit_counter;   /* two words, zero before the first launch: [0] units handed out beyond the first
                                  gridDim.x, [1] CTAs finished (the last one leaves both at zero again)     */
+    /* single-capture launches of the streaming path: the LAST CTA to finish also does k_spectrum_finalize's job
+     * (same arithmetic, same order), which saves a launch per ring slot.  final_out = null: separate finalize kernel. */
+    float *final_out;         /* 1024 floats                                                     */
+    const float *carry;       /* optional 1024 floats (may alias final_out)                      */
+    float final_scale, carry_scale;
     float ema_log2_decay;     /* log2(1 - beta), EMA only                                        */
     float ema_beta;
 };
@@ -312,11 +317,31 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         for (int w = 0; w < B200_SPEC_WARPS; ++w) s += s_red[w * (32 * B200_SPEC_XP * 2) + k];
         out[k] = s;
     }
+    if (p.final_out) __threadfence(); /* the partial must be visible to whichever CTA finishes last */
     unit_g = s_cvt[2];
     __syncthreads(); /* the reduction buffer and s_cvt[2] are free again */
     } /* units */
-    /* the last CTA out leaves the hand-out counter at zero for the next launch (atomicInc wraps its own word) */
-    if (tid == 0 && atomicInc(p.unit_counter + 1, gridDim.x - 1u) == gridDim.x - 1u) p.unit_counter[0] = 0u;
+    /* the last CTA out leaves the hand-out counter at zero for the next launch (atomicInc wraps its own word) ... */
+    if (tid == 0) {
+        const bool last = atomicInc(p.unit_counter + 1, gridDim.x - 1u) == gridDim.x - 1u;
+        if (last) p.unit_counter[0] = 0u;
+        s_cvt[3] = last ? 1u : 0u;
+    }
+    /* ... and, for a single capture of the streaming path, adds up the partials: out = scale * sum_i partial_i +
+     * carry_scale * carry, units in fixed order -- k_spectrum_finalize without the extra launch */
+    if (p.final_out) {
+        __syncthreads();
+        if (s_cvt[3]) {
+            __threadfence();
+            for (int k = tid; k < 1024; k += B200_SPEC_THREADS) {
+                float sum = 0.0f;
+                for (uint32_t i = 0; i < p.total_units; ++i) sum += __ldcg(p.partials + (uint64_t)i * 1024u + k);
+                float r = sum * p.final_scale;
+                if (p.carry) r = fmaf(p.carry[k], p.carry_scale, r);
+                p.final_out[k] = r;
+            }
+        }
+    }
 }
 
 /* out[c][k] = scale * sum_i partials[c][i][k] + carry_scale * carry[k]  (fixed order) */

@@ -272,6 +272,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __ldg(const float *p) { return *p; }
+static inline float __ldcg(const float *p) { return *p; }
 static inline unsigned __ldg(const unsigned *p) { return *p; }
 static inline unsigned short __ldg(const unsigned short *p) { return *p; }
 static inline uint4 __ldg(const uint4 *p) { return *p; }

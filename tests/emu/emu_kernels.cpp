@@ -38,6 +38,14 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
     p.total_units = ctas * n_captures;
     uint32_t unit_counter[2] = {0u, 0u};
     p.unit_counter = unit_counter;
+    p.final_out = nullptr;
+    p.carry = nullptr;
+    p.final_scale = p.carry_scale = 0.0f;
+    std::vector<float> folded(1024, 0.0f);
+    if (n_captures == 1) { /* the streaming form: the last CTA finalizes; must equal k_spectrum_finalize bit for bit */
+        p.final_out = folded.data();
+        p.final_scale = ema ? 1.0f : 1.0f / (float)frames;
+    }
     p.ema_beta = beta;
     p.ema_log2_decay = log2f(1.0f - beta);
     /* a persistent grid smaller than the number of units: every CTA walks several units */
@@ -48,6 +56,7 @@ int emu_spectrum(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes
     if (unit_counter[0] != 0u || unit_counter[1] != 0u) return -2; /* the last CTA must leave the hand-out counter at zero */
     emu::launch(dim3(4, n_captures), dim3(256), 0,
                 [&] { k_spectrum_finalize(partials.data(), ctas, scale, nullptr, 0.0f, out); });
+    if (n_captures == 1 && memcmp(folded.data(), out, 1024 * sizeof(float)) != 0) return -3;
     return (int)frames;
 }
 

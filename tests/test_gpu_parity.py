@@ -423,7 +423,9 @@ def test_small_blocks_are_coalesced_into_ring_slots(sdr_lib, g):
             assert s.counters()["blocks_in"] == iq.size // 512 and s.counters()["bytes_in"] == iq.size
         assert frames == (iq.size - 2048) // 1024 + 1
         spec_check(spec, g.spectrum(iq)[0])
-    assert launches["coalesced"] <= 4 and launches["per_block"] >= 500
+    # per block: one k_spectrum launch per completed frame (every second 512-byte block); the streaming form folds the
+    # finalize into the kernel's last CTA, so there is no second launch per slot
+    assert launches["coalesced"] <= 4 and launches["per_block"] >= 250
     with pytest.raises(sdr_lib.B200SdrError) as ei:
         sdr_lib.B200Sdr(slot_bytes=4096, submit_bytes=8192)
     assert ei.value.status == sdr_lib.NOT_SUPPORTED
