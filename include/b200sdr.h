@@ -55,6 +55,14 @@ extern "C" {
 #define B200SDR_AVG_MEAN 0u /* P[k] = (1/F) sum_m |X_m[k]|^2                              */
 #define B200SDR_AVG_EMA  1u /* P <- (1-beta) P + beta |X_m|^2 per frame, P starts at 0    */
 
+/* stage-1 FIR engine of the batched WBFM path (b200sdr_batch_wbfm_dev, b200sdr_batch_host).
+ * FP32: input-partitioned FIR on the CUDA cores, packed fp32x2 FMAs, taps in registers (csrc/wbfm.cuh) -- the default and
+ *       the only engine of the streaming path.
+ * TENSOR: the FIR as an exact u8 x s8 -> s32 banded-Toeplitz product on the tensor cores (tcgen05.mma kind::i8, TMEM),
+ *       taps as three signed 8-bit slices (csrc/wbfm_tc.cuh); same results within the tolerances of the parity tests. */
+#define B200SDR_FIR_ENGINE_FP32   0u
+#define B200SDR_FIR_ENGINE_TENSOR 1u
+
 #define B200SDR_NFFT 1024u
 #define B200SDR_HOP  512u
 
@@ -100,7 +108,8 @@ typedef struct b200sdr_config {
                                bytes are pending or the next block would not fit; 0 = slot_bytes.
                                The firmware's 512-byte URBs (usbh_rtlsdr.c:230) then cost one
                                memcpy each; 4 submits every block on its own.                 */
-    uint32_t reserved[6];
+    uint32_t fir_engine;    /* B200SDR_FIR_ENGINE_*: how the batched WBFM path computes its first (/10, 80-tap) FIR  */
+    uint32_t reserved[5];
 } b200sdr_config;
 
 /* Fill *cfg with defaults: device 0, all chains, Hann, mean, 8 slots of 262144 bytes. */
@@ -268,6 +277,13 @@ B200SDR_API int32_t b200sdr_render_waterfall_dev(b200sdr_ctx *ctx, const float *
 B200SDR_API int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *out, uint32_t capacity,
                                      uint32_t *n_taps);
 B200SDR_API int32_t b200sdr_get_window(b200sdr_ctx *ctx, uint32_t window, float *out1024);
+
+/* Parity hook of the TENSOR FIR engine: run it over ONE device-resident capture (len % 16 == 0) and return the raw
+ * 32-bit accumulators of its first tile, acc_host[row r][32 s + 2 i + c] = sum_t q_s[t] u[2 (10 (16 r + i) - t) + c]
+ * (128 x 96; rows 125..127 unused), the three signed 8-bit tap slices (slices_host[3][80], may be NULL) and the
+ * exponent e with h[t] 2^e = q0 2^-7 + q1 2^-14 + q2 2^-21 (may be NULL): the integer product must be bit-exact. */
+B200SDR_API int32_t b200sdr_debug_wbfm_tc_acc(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64_t len, int32_t *acc_host,
+                                              int8_t *slices_host, int32_t *exponent);
 
 /* Read back the device copy of the most recently ingested block (ingest parity checks). */
 B200SDR_API int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capacity, uint32_t *len);

@@ -27,6 +27,8 @@ from .binding import (  # noqa: F401
     SYNTH_MULTITONE,
     SYNTH_WBFM,
     SYNTH_AM,
+    FIR_ENGINE_FP32,
+    FIR_ENGINE_TENSOR,
     OK,
     BUSY,
     FAIL,

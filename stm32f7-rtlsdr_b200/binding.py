@@ -17,6 +17,7 @@ CHAIN_SPECTRUM, CHAIN_WBFM, CHAIN_AM, CHAIN_COUNTER = 1, 2, 4, 8
 WINDOW_RECT, WINDOW_HANN, WINDOW_BLACKMAN = 0, 1, 2
 AVG_MEAN, AVG_EMA = 0, 1
 SYNTH_COUNTER, SYNTH_MULTITONE, SYNTH_WBFM, SYNTH_AM = 0, 1, 2, 3
+FIR_ENGINE_FP32, FIR_ENGINE_TENSOR = 0, 1
 
 _STATUS = {0: "OK", 1: "BUSY", 2: "FAIL", 3: "NOT_SUPPORTED", 4: "UNRECOVERED_ERROR"}
 
@@ -39,7 +40,8 @@ class Config(C.Structure):
         ("slot_bytes", C.c_uint32),
         ("audio_capacity", C.c_uint32),
         ("submit_bytes", C.c_uint32),
-        ("reserved", C.c_uint32 * 6),
+        ("fir_engine", C.c_uint32),
+        ("reserved", C.c_uint32 * 5),
     ]
 
 
@@ -92,6 +94,7 @@ def load_library():
         "b200sdr_get_taps": (i32, [vp, u32, f32p, u32, C.POINTER(u32)]),
         "b200sdr_get_window": (i32, [vp, u32, f32p]),
         "b200sdr_debug_last_block": (i32, [vp, u8p, u32, C.POINTER(u32)]),
+        "b200sdr_debug_wbfm_tc_acc": (i32, [vp, u8p, u64, vp, vp, C.POINTER(C.c_int32)]),
         "b200sdr_synth_fill_dev": (i32, [vp, u8p, u32, u64, u32, u64]),
         "b200sdr_synth_fill_host": (i32, [u8p, u32, u64, u32, u64]),
         "b200sdr_dev_alloc": (i32, [vp, u64, C.POINTER(vp)]),
@@ -246,13 +249,14 @@ class B200Sdr:
 
     def __init__(self, device=0, chains=CHAIN_SPECTRUM | CHAIN_WBFM | CHAIN_AM, window=WINDOW_HANN,
                  avg_mode=AVG_MEAN, ema_beta=0.1, ring_slots=8, slot_bytes=262144, audio_capacity=1 << 20,
-                 submit_bytes=0):
+                 submit_bytes=0, fir_engine=FIR_ENGINE_FP32):
         self.lib = load_library()
         cfg = Config()
         self.lib.b200sdr_default_config(C.byref(cfg))
         cfg.device, cfg.chains, cfg.window, cfg.avg_mode = device, chains, window, avg_mode
         cfg.ema_beta, cfg.ring_slots, cfg.slot_bytes, cfg.audio_capacity = ema_beta, ring_slots, slot_bytes, audio_capacity
         cfg.submit_bytes = submit_bytes
+        cfg.fir_engine = fir_engine
         self.cfg = cfg
         self.ctx = C.c_void_p()
         rc = self.lib.b200sdr_create(C.byref(cfg), C.byref(self.ctx))
@@ -333,6 +337,21 @@ class B200Sdr:
         n = C.c_uint32()
         self._check(self.lib.b200sdr_debug_last_block(self.ctx, out.ctypes.data, capacity, C.byref(n)), "b200sdr_debug_last_block")
         return out[: min(n.value, capacity)].copy(), n.value
+
+    def debug_wbfm_tc_acc(self, iq):
+        """TENSOR FIR engine over one capture: (raw accumulators of the first tile [128][96] int32, tap slices [3][80] int8, e)."""
+        iq = _u8(iq)
+        d = self.dev_alloc(iq.size)
+        try:
+            self.to_dev(d, iq)
+            acc = np.zeros((128, 96), np.int32)
+            q = np.zeros((3, 80), np.int8)
+            e = C.c_int32(0)
+            self._check(self.lib.b200sdr_debug_wbfm_tc_acc(self.ctx, d, iq.size, acc.ctypes.data, q.ctypes.data, C.byref(e)),
+                        "b200sdr_debug_wbfm_tc_acc")
+        finally:
+            self.dev_free(d)
+        return acc, q, e.value
 
     # -- device memory ----------------------------------------------------------------------
     def dev_alloc(self, nbytes):

@@ -65,6 +65,9 @@ struct b200sdr_ctx {
     float *d_partials_stream = nullptr; size_t partials_stream_floats = 0; /* streaming k_spectrum's own workspace ...  */
     uint32_t *d_unit_counter_stream = nullptr;                             /* ... and hand-out counter (it may run next to a batch launch) */
     bool failed = false;     /* sticky: a chain failed after its H2D was enqueued (see commit_slot) */
+    uint8_t *d_tc_image = nullptr;  /* tensor-core FIR engine (wbfm_tc.cuh): the B operand as it lies in shared memory ... */
+    uint32_t *d_tc_error = nullptr; /* ... and the word its bounded waits report a protocol error in                      */
+    bool tc_launched = false;       /* a k_wbfm_tc launch since the last check of d_tc_error                              */
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     uint64_t launches = 0;
     char err[256] = {0};
@@ -209,9 +212,54 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     return B200SDR_OK;
 }
 
+/* cfg.fir_engine = TENSOR: stage 1 on the tensor cores (wbfm_tc.cuh); `dbg_acc` = optional raw accumulators (tests) */
+int launch_wbfm_tc_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_bytes, float *audio,
+                         float *disc, int32_t *dbg_acc = nullptr)
+{
+    b200::FmTcPlan pl = b200::plan_wbfm_tc(len_bytes, n_captures, (uint32_t)ctx->sm_count);
+    if (pl.n_tiles == 0) return B200SDR_OK;
+    FmTcParams p{};
+    p.iq = iq_dev;
+    p.capture_stride = len_bytes;
+    p.capture_bytes = len_bytes;
+    p.m1 = pl.m1;
+    p.n_tiles = pl.n_tiles;
+    p.total_rows = pl.total_rows;
+    p.tiles_per_segment = pl.tiles_per_segment;
+    p.segments = pl.segments;
+    p.n_captures = n_captures;
+    p.audio = audio;
+    p.audio_stride = b200::wbfm_audio_len(len_bytes);
+    p.disc = disc;
+    p.disc_stride = pl.m1;
+    p.b_image = ctx->d_tc_image;
+    p.error = ctx->d_tc_error;
+    p.dbg_acc = dbg_acc;
+    { const char *e = getenv("B200SDR_TC_DEBUG"); p.dbg_flags = e ? (uint32_t)atoi(e) : 0u; } /* timing experiments (tools/tc_check.py) */
+    k_wbfm_tc<<<dim3(pl.grid), B200_TC_THREADS, B200_TC_SMEM_BYTES, ctx->s_compute>>>(p);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->tc_launched = true;
+    return B200SDR_OK;
+}
+/* after the compute stream has been synchronised: did a bounded wait of k_wbfm_tc expire? */
+int check_tc_error(b200sdr_ctx *ctx)
+{
+    if (!ctx->tc_launched) return B200SDR_OK;
+    ctx->tc_launched = false;
+    uint32_t code = 0;
+    CU(cudaMemcpy(&code, ctx->d_tc_error, sizeof code, cudaMemcpyDeviceToHost));
+    if (code == 0) return B200SDR_OK;
+    CU(cudaMemset(ctx->d_tc_error, 0, sizeof code));
+    char msg[96];
+    snprintf(msg, sizeof msg, "k_wbfm_tc: pipeline wait expired (role %u); results of that launch are invalid", code);
+    return fail(ctx, B200SDR_FAIL, msg);
+}
+
 int launch_wbfm_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_bytes, float *audio,
                       float *disc)
 {
+    if (ctx->cfg.fir_engine == B200SDR_FIR_ENGINE_TENSOR) return launch_wbfm_tc_batch(ctx, iq_dev, n_captures, len_bytes, audio, disc);
     b200::FmPlan pl = b200::plan_wbfm_batch(len_bytes, n_captures, (uint32_t)ctx->sm_count);
     if (pl.n_tiles == 0) return B200SDR_OK;
     FmParams p{};
@@ -587,6 +635,7 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     if ((cfg.chains & B200SDR_CHAIN_WBFM) && cfg.audio_capacity < cfg.slot_bytes / 100 + 16) cfg.audio_capacity = cfg.slot_bytes / 100 + 16;
     if ((cfg.chains & B200SDR_CHAIN_AM) && cfg.audio_capacity < cfg.slot_bytes / 600 + 16) cfg.audio_capacity = cfg.slot_bytes / 600 + 16;
     if (cfg.submit_bytes > cfg.slot_bytes) return B200SDR_NOT_SUPPORTED;
+    if (cfg.fir_engine > B200SDR_FIR_ENGINE_TENSOR) return B200SDR_NOT_SUPPORTED;
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || cfg.device < 0 || cfg.device >= n_dev)
@@ -632,6 +681,7 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
     CK(cudaFuncSetAttribute(k_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_SPEC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_SPEC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_wbfm, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_FM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_wbfm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_TC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_am_front, cudaFuncAttributeMaxDynamicSharedMemorySize, B200_AM_SMEM_BYTES));
 
     /* constants */
@@ -650,6 +700,16 @@ int32_t b200sdr_create(const b200sdr_config *cfg_in, b200sdr_ctx **out_ctx)
         FmTaps ft{};
         b200::fill_fm_taps(ft);
         CK(cudaMemcpyToSymbol(c_fm_taps, &ft, sizeof ft));
+        {
+            FmTcConsts tc{};
+            std::vector<uint8_t> image(B200_TC_B_BYTES);
+            b200::fill_fm_tc(tc, image.data());
+            CK(cudaMemcpyToSymbol(c_fm_tc, &tc, sizeof tc));
+            CK(cudaMalloc((void **)&ctx->d_tc_image, B200_TC_B_BYTES));
+            CK(cudaMemcpy(ctx->d_tc_image, image.data(), B200_TC_B_BYTES, cudaMemcpyHostToDevice));
+            CK(cudaMalloc((void **)&ctx->d_tc_error, sizeof(uint32_t)));
+            CK(cudaMemset(ctx->d_tc_error, 0, sizeof(uint32_t)));
+        }
         AmTaps at{};
         b200::fill_am_taps(at);
         CK(cudaMemcpyToSymbol(c_am_taps, &at, sizeof at));
@@ -725,7 +785,7 @@ int32_t b200sdr_destroy(b200sdr_ctx *ctx)
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
-    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc, ctx->d_unit_counter, ctx->d_unit_counter_stream, ctx->d_partials_stream,
+    void *dev_ptrs[] = {ctx->d_stream, ctx->d_spec_acc, ctx->d_unit_counter, ctx->d_unit_counter_stream, ctx->d_partials_stream, ctx->d_tc_image, ctx->d_tc_error,
                         ctx->d_fm_state, ctx->d_amf_state, ctx->d_amb_state, ctx->d_am_env_stream, ctx->fm_fifo.d_buf,
                         ctx->am_fifo.d_buf, ctx->fm_fifo.d_spare, ctx->am_fifo.d_spare, ctx->d_window[0], ctx->d_window[1], ctx->d_window[2], ctx->d_twiddle,
                         ctx->d_lut, ctx->d_partials, ctx->d_env, ctx->d_thresholds, ctx->d_res_spec, ctx->d_res_fm,
@@ -820,7 +880,7 @@ int32_t b200sdr_sync(b200sdr_ctx *ctx)
     int jrc = join_chains(ctx);
     if (jrc) return jrc;
     CU(cudaStreamSynchronize(ctx->s_compute));
-    return B200SDR_OK;
+    return check_tc_error(ctx);
 }
 
 int32_t b200sdr_reset(b200sdr_ctx *ctx)
@@ -891,6 +951,34 @@ int32_t b200sdr_debug_last_block(b200sdr_ctx *ctx, uint8_t *out, uint32_t capaci
     if (n) CU(cudaMemcpy(out, ctx->d_stream + ctx->last_pos + ctx->last_off, n, cudaMemcpyDeviceToHost));
     if (len) *len = ctx->last_len;
     return B200SDR_OK;
+}
+
+int32_t b200sdr_debug_wbfm_tc_acc(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64_t len, int32_t *acc_host, int8_t *slices_host,
+                                  int32_t *exponent)
+{
+    if (!ctx || !iq_dev || !acc_host) return B200SDR_FAIL;
+    if (len == 0 || (len & 15u) || ((uintptr_t)iq_dev & 15u)) return B200SDR_NOT_SUPPORTED;
+    DeviceGuard guard(ctx->device);
+    int32_t *d_acc = nullptr;
+    float *d_audio = nullptr;
+    CU(cudaMalloc((void **)&d_acc, 128 * 96 * sizeof(int32_t)));
+    CU(cudaMemset(d_acc, 0, 128 * 96 * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc((void **)&d_audio, (b200::wbfm_audio_len(len) + 4) * sizeof(float));
+    int rc = e == cudaSuccess ? launch_wbfm_tc_batch(ctx, iq_dev, 1, len, d_audio, nullptr, d_acc) : fail(ctx, B200SDR_FAIL, "cudaMalloc", e);
+    if (!rc && cudaStreamSynchronize(ctx->s_compute) != cudaSuccess) rc = fail(ctx, B200SDR_FAIL, "k_wbfm_tc", cudaGetLastError());
+    if (!rc) rc = check_tc_error(ctx);
+    if (!rc && cudaMemcpy(acc_host, d_acc, 128 * 96 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200SDR_FAIL;
+    cudaFree(d_acc);
+    cudaFree(d_audio);
+    if (slices_host || exponent) {
+        FmTcConsts tc{};
+        int8_t q[3][B200_FM_T1];
+        int ex = 0;
+        b200::fill_fm_tc(tc, nullptr, q, &ex);
+        if (slices_host) memcpy(slices_host, q, sizeof q);
+        if (exponent) *exponent = ex;
+    }
+    return rc;
 }
 
 /* ---- batched, device-resident -------------------------------------------------------------- */

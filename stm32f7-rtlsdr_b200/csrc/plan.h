@@ -6,10 +6,12 @@
 #define B200_PLAN_H
 
 #include <cstdint>
+#include <cstring>
 
 #include "filter_design.h"
 #include "spectrum.cuh"
 #include "wbfm.cuh"
+#include "wbfm_tc.cuh"
 #include "am.cuh"
 
 namespace b200 {
@@ -119,6 +121,89 @@ inline void fill_fm_taps(FmTaps &t)
     t.a12 = (float)a12;
     for (int s = 0; s < 5; ++s) t.a12pow[s] = (float)std::pow(a12, double(1 << s));
     t.a384 = (float)std::pow(a12, 32.0);
+}
+
+/* ---- WBFM, tensor-core engine (wbfm_tc.cuh) ---- */
+struct FmTcPlan {
+    uint32_t n_tiles, total_rows, tiles_per_segment, segments, grid;
+    uint64_t m1;
+};
+inline FmTcPlan plan_wbfm_tc(uint64_t len_bytes, uint32_t n_captures, uint32_t sm_count)
+{
+    FmTcPlan pl{};
+    const uint64_t n = len_bytes / 2;
+    pl.m1 = ceil_div(n, 10);
+    pl.total_rows = (uint32_t)ceil_div(n, B200_TC_ROW_SAMPLES);
+    pl.n_tiles = (uint32_t)ceil_div(pl.total_rows, B200_TC_ROWS);
+    /* work items = (capture, segment), handed to one persistent CTA per SM round-robin: enough items for ~8 rounds, but
+     * segments of at least 40 tiles in a batch (8 for a few captures): every segment after the first pre-rolls one tile */
+    const uint64_t want = ceil_div((uint64_t)sm_count * 8, n_captures ? n_captures : 1);
+    const uint64_t tps_min = n_captures >= 16 ? 40 : 8;
+    uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
+    if (tps < tps_min) tps = tps_min;
+    if (tps > pl.n_tiles) tps = pl.n_tiles ? pl.n_tiles : 1;
+    pl.tiles_per_segment = (uint32_t)tps;
+    pl.segments = (uint32_t)ceil_div(pl.n_tiles, tps);
+    if (pl.segments == 0) pl.segments = 1;
+    const uint64_t items = (uint64_t)pl.segments * n_captures;
+    pl.grid = (uint32_t)(items < sm_count ? items : sm_count);
+    return pl;
+}
+/* The stage-1 taps as three signed 8-bit slices, h[t] 2^e = q0 2^-7 + q1 2^-14 + q2 2^-21 (+ at most 2^-22), the
+ * constants of the slice combine, and the B operand as it lies in shared memory (B200_TC_B_BYTES, 128B swizzle).
+ * q[s][t] (optional) receives the slices, *e_out the exponent. */
+inline void fill_fm_tc(FmTcConsts &c, uint8_t *image, int8_t (*q_out)[B200_FM_T1] = nullptr, int *e_out = nullptr)
+{
+    const std::vector<double> h1 = design_taps(0), h2 = design_taps(1);
+    double hmax = 0.0;
+    for (double v : h1) hmax = std::fabs(v) > hmax ? std::fabs(v) : hmax;
+    int e = 0;
+    while (std::ldexp(hmax, e + 1 + 7) <= 127.0) ++e; /* largest e with |h| 2^e 2^7 <= 127 */
+    int8_t q[3][B200_FM_T1];
+    double sum[3] = {0, 0, 0};
+    for (int t = 0; t < B200_FM_T1; ++t) {
+        double r = std::ldexp(h1[t], e);
+        for (int s = 0; s < 3; ++s) {
+            double v = std::nearbyint(std::ldexp(r, 7 * (s + 1)));
+            if (v > 127) v = 127;
+            if (v < -127) v = -127;
+            q[s][t] = (int8_t)v;
+            r -= std::ldexp(v, -7 * (s + 1));
+            sum[s] += v;
+        }
+    }
+    const double c0 = std::ldexp(1.0, -7 - e), c1 = std::ldexp(1.0, -14 - e), c2 = std::ldexp(1.0, -21 - e);
+    c.c0 = (float)c0; c.c1 = (float)c1; c.c2 = (float)c2;
+    c.b0 = (float)(127.5 * sum[0]);
+    c.k12 = (float)(-127.5 * (c1 * sum[1] + c2 * sum[2]));
+    for (int i = 0; i < 16; ++i) {
+        double s0 = 0, s1 = 0, s2 = 0;
+        for (int t = 0; t < B200_FM_T1 && t <= 10 * i; ++t) { s0 += q[0][t]; s1 += q[1][t]; s2 += q[2][t]; }
+        c.b0_first[i] = (float)(127.5 * s0);
+        c.k12_first[i] = (float)(-127.5 * (c1 * s1 + c2 * s2));
+    }
+    const double alpha = deemph_alpha(), a = 1.0 - alpha, a16 = std::pow(a, B200_TC_OPR);
+    c.alpha = (float)alpha;
+    for (int i = 0; i < 16; ++i) c.apow[i] = (float)std::pow(a, i + 1);
+    c.a16 = (float)a16;
+    for (int s = 0; s < 5; ++s) c.a16pow[s] = (float)std::pow(a16, double(1 << s));
+    c.a512 = (float)std::pow(a16, 32.0);
+    for (int t = 0; t < B200_FM_T2; ++t) c.h2[t] = (float)h2[t];
+    if (image) {
+        memset(image, 0, B200_TC_B_BYTES);
+        for (int s = 0; s < 3; ++s)
+            for (int i = 0; i < B200_TC_OPR; ++i)
+                for (int comp = 0; comp < 2; ++comp) {
+                    const int n = 32 * s + 2 * i + comp;
+                    for (int kap = 0; kap < B200_TC_K_BYTES / 2; ++kap) {
+                        const int t = 80 + 10 * i - kap;
+                        if (t < 0 || t >= B200_FM_T1) continue;
+                        image[B200_TC_OP_OFF(B200_TC_N, n, 2 * kap + comp)] = (uint8_t)q[s][t];
+                    }
+                }
+    }
+    if (q_out) memcpy(q_out, q, sizeof q);
+    if (e_out) *e_out = e;
 }
 
 /* ---- AM ---- */

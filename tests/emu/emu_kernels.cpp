@@ -122,6 +122,43 @@ int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, v
     return 0;
 }
 
+/* WBFM, tensor-core engine (csrc/wbfm_tc.cuh): the epilogue threads run on the host, the u8 x s8 -> s32 product is taken
+ * from the same B image and source addressing (exact, like the hardware).  dbg_acc: optional [128][96] raw accumulators
+ * of tile 0 of capture 0; q_out: optional [3][80] tap slices; returns the tap exponent e. */
+int emu_wbfm_tc_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, uint32_t tiles_per_segment,
+                      float *audio, float *disc, int32_t *dbg_acc, int8_t *q_out)
+{
+    static std::vector<uint8_t> image(B200_TC_B_BYTES);
+    int e = 0;
+    b200::fill_fm_tc(c_fm_tc, image.data(), (int8_t(*)[B200_FM_T1])q_out, &e);
+    b200::FmTcPlan pl = b200::plan_wbfm_tc(len_each_bytes, n_captures, 148);
+    if (tiles_per_segment) {
+        pl.tiles_per_segment = tiles_per_segment;
+        pl.segments = (uint32_t)b200::ceil_div(pl.n_tiles, tiles_per_segment);
+    }
+    FmTcParams p{};
+    p.iq = iq;
+    p.capture_stride = len_each_bytes;
+    p.capture_bytes = len_each_bytes;
+    p.m1 = pl.m1;
+    p.n_tiles = pl.n_tiles;
+    p.total_rows = pl.total_rows;
+    p.tiles_per_segment = pl.tiles_per_segment;
+    p.segments = pl.segments;
+    p.n_captures = n_captures;
+    p.audio = audio;
+    p.audio_stride = b200::wbfm_audio_len(len_each_bytes);
+    p.disc = disc;
+    p.disc_stride = pl.m1;
+    p.b_image = image.data();
+    p.error = nullptr;
+    p.dbg_acc = dbg_acc;
+    /* fewer CTAs than work items: every CTA walks several */
+    const uint32_t items = pl.segments * n_captures;
+    emu::launch(dim3(items > 2 ? 2 : items, 1), dim3(B200_TC_EPI), B200_TC_SMEM_BYTES, [&] { k_wbfm_tc(p); });
+    return e;
+}
+
 int emu_sizeof_fm_state(void) { return (int)sizeof(FmState); }
 int emu_fm_chunk(void) { return B200_FM_CHUNK; }
 

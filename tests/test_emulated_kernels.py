@@ -21,6 +21,7 @@ def emu():
     e.emu_spectrum.argtypes = [vp, u32, u64, vp, u32, C.c_int, C.c_float, vp]
     e.emu_wbfm_batch.argtypes = [vp, u32, u64, u32, vp, vp]
     e.emu_wbfm_stream.argtypes = [vp, u32, u64, vp, vp, vp, vp, u32]
+    e.emu_wbfm_tc_batch.argtypes = [vp, u32, u64, u32, vp, vp, vp, vp]
     e.emu_am_batch.argtypes = [vp, u32, u64, u32, vp, vp]
     e.emu_am_stream.argtypes = [vp, u32, u64, vp, vp, vp, vp, u32]
     return e
@@ -195,6 +196,66 @@ def test_wbfm_kernel_logic(emu, g, n, ncap, tps):
         ga, gd = g.wbfm(iq[c * nb:(c + 1) * nb], want_disc=True)
         assert np.max(np.abs(wrap_phase(disc[c * m1:(c + 1) * m1] - gd))) < 1e-5
         assert np.max(np.abs(audio[c * m2:(c + 1) * m2] - ga)) < 1e-5
+
+
+@pytest.mark.parametrize("n,ncap,tps", [(160 * 125 * 3, 1, 0), (160 * 125 * 2 + 1232, 2, 1), (20000 + 160 * 7 + 8, 1, 2),
+                                        (8, 1, 0), (160 * 125, 3, 0), (50008, 1, 1)])
+def test_wbfm_tensor_engine_logic(emu, g, n, ncap, tps):
+    """csrc/wbfm_tc.cuh under the host emulation: the banded-Toeplitz product (three signed 8-bit tap slices on the raw
+    bytes, exact integers -- the part the tensor cores do on the device), the 128B-swizzled B image, the slice combine
+    with the offset removed exactly, the first row of a capture (zero-filled history), ragged ends, segments with
+    pre-roll, several work items per CTA; against oracle B."""
+    nb = 2 * n
+    iq = padded(g.synth(ncap, nb, SYNTH_WBFM, 11))
+    m1 = -(-n // 10)
+    m2 = -(-m1 // 5)
+    audio = np.full(m2 * ncap, np.nan, np.float32)
+    disc = np.full(m1 * ncap, np.nan, np.float32)
+    acc = np.zeros((128, 96), np.int32)
+    q = np.zeros((3, 80), np.int8)
+    e = emu.emu_wbfm_tc_batch(iq.ctypes.data, ncap, nb, tps, audio.ctypes.data, disc.ctypes.data, acc.ctypes.data, q.ctypes.data)
+    # the slices reproduce the float64 taps to 2^-22 / 2^e, i.e. 3.6e-7 of the largest tap
+    h = g.taps(0)
+    hq = (q[0] * 2.0**-7 + q[1] * 2.0**-14 + q[2] * 2.0**-21) / 2.0**e
+    assert np.max(np.abs(hq - h)) <= 2.0**-22 / 2.0**e * 1.001 and np.max(np.abs(hq - h)) < 4e-7 * np.max(np.abs(h))
+    # raw accumulators of tile 0 = the integer FIR of the raw bytes, slice by slice (row 0: zero-filled history)
+    u = iq[:nb].astype(np.int64)
+    for r in (0, 1, 7, 124):
+        for i in (0, 3, 15):
+            m = 16 * r + i
+            if 10 * m >= n:
+                continue
+            for c in (0, 1):
+                for s in range(3):
+                    want = sum(int(q[s][t]) * int(u[2 * (10 * m - t) + c]) for t in range(80) if 0 <= 10 * m - t < n)
+                    assert acc[r, 32 * s + 2 * i + c] == want, (r, i, c, s)
+    for c in range(ncap):
+        ga, gd = g.wbfm(iq[c * nb:(c + 1) * nb], want_disc=True)
+        derr = np.abs(wrap_phase(disc[c * m1:(c + 1) * m1] - gd))
+        # outputs 1..7 are the filter's rise from nothing through its outermost taps (1e-3 of the largest and smaller),
+        # where the 2^-22 tap quantisation is 1e-4 of the tap: phase within 1e-4 rad there, 1e-5 everywhere else
+        assert np.max(derr[:8]) < 1e-4 and (derr.size <= 8 or np.max(derr[8:]) < 1e-5)
+        assert np.max(np.abs(audio[c * m2:(c + 1) * m2] - ga)) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["fullscale_tone", "half_lsb_rotation", "tone_on_dc"])
+def test_wbfm_tensor_engine_extreme_bytes(emu, g, name):
+    """the smallest and the largest phasors a u8 stream can carry: the offset cancels in exact integer / half-integer
+    arithmetic here, so the bound is the north_star's 1e-4 rad with room to spare"""
+    n = 30720 + 1208
+    nb = 2 * n
+    const, rot = extreme_patterns(nb)
+    iq = padded(rot[name])
+    m1 = -(-n // 10)
+    m2 = -(-m1 // 5)
+    audio = np.full(m2, np.nan, np.float32)
+    disc = np.full(m1, np.nan, np.float32)
+    emu.emu_wbfm_tc_batch(iq.ctypes.data, 1, nb, 1, audio.ctypes.data, disc.ctypes.data, None, None)
+    ga, gd = g.wbfm(iq[:nb], want_disc=True)
+    # the first outputs of a capture are the filter's rise from nothing (|y| ~ 1e-6): skip what the fp32 engine's test skips
+    derr, aerr = np.max(np.abs(wrap_phase(disc - gd))[16:]), np.max(np.abs(audio - ga)[8:])
+    print(name, "disc err", derr, "audio err", aerr)
+    assert derr < 2e-5 and aerr < 2e-5
 
 
 @pytest.mark.parametrize("tps", [0, 1, 2])

@@ -561,7 +561,7 @@ def test_full_size_capture_batch(sdr, g):
 def test_kernel_launch_counter_moves(sdr, g):
     before = sdr.kernel_launches()
     sdr.spectrum(g.synth(1, 262144, SYNTH_MULTITONE, 0))
-    assert sdr.kernel_launches() >= before + 2
+    assert sdr.kernel_launches() >= before + 1  # one 256 KiB block: k_spectrum with the finalize folded into its last CTA
 
 
 # ------------------------------------------------------------------------------- more edge cases
