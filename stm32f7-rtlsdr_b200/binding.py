@@ -339,12 +339,12 @@ class B200Sdr:
         return out[: min(n.value, capacity)].copy(), n.value
 
     def debug_wbfm_tc_acc(self, iq):
-        """TENSOR FIR engine over one capture: (raw accumulators of the first tile [128][96] int32, tap slices [3][80] int8, e)."""
+        """TENSOR FIR engine over one capture: (raw accumulators of the first tile [128][112] int32, tap slices [3][80] int8, e)."""
         iq = _u8(iq)
         d = self.dev_alloc(iq.size)
         try:
             self.to_dev(d, iq)
-            acc = np.zeros((128, 96), np.int32)
+            acc = np.zeros((128, 112), np.int32)
             q = np.zeros((3, 80), np.int8)
             e = C.c_int32(0)
             self._check(self.lib.b200sdr_debug_wbfm_tc_acc(self.ctx, d, iq.size, acc.ctypes.data, q.ctypes.data, C.byref(e)),

@@ -11,6 +11,7 @@
  * No CPU fallback: every result comes from the CUDA kernels in this directory; if CUDA is not
  * usable, b200sdr_create fails.
  */
+#include <cuda.h> /* CUtensorMap + the cuTensorMapEncodeTiled prototype; the entry point comes from the runtime, libcuda is not linked */
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -212,6 +213,35 @@ int launch_spectrum(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures
     return B200SDR_OK;
 }
 
+/* the driver's tensor-map encoder through the runtime (no -lcuda) */
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+tensor_map_encode_fn tensor_map_encoder()
+{
+    static const tensor_map_encode_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (tensor_map_encode_fn)p;
+    }();
+    return fn;
+}
+/* The batch as TMA sees it: (320 bytes, rows of a capture, captures), u8, boxes of 64 bytes x 125 rows, 64B swizzle.
+ * Only whole rows are inside the tensor, so everything outside a capture reads as zero.  false: use the cp.async path. */
+bool make_tc_tensor_map(CUtensorMap *map, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_bytes)
+{
+    memset(map, 0, sizeof *map);
+    const tensor_map_encode_fn enc = tensor_map_encoder();
+    const uint64_t rows = len_bytes / B200_TC_ROW_BYTES;
+    if (!enc || rows == 0 || getenv("B200SDR_TC_NO_TMA")) return false;
+    const cuuint64_t dims[3] = {B200_TC_ROW_BYTES, rows, n_captures};
+    const cuuint64_t strides[2] = {B200_TC_ROW_BYTES, len_bytes};
+    const cuuint32_t box[3] = {64, B200_TC_ROWS, 1}, elem[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)iq_dev, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 /* cfg.fir_engine = TENSOR: stage 1 on the tensor cores (wbfm_tc.cuh); `dbg_acc` = optional raw accumulators (tests) */
 int launch_wbfm_tc_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_captures, uint64_t len_bytes, float *audio,
                          float *disc, int32_t *dbg_acc = nullptr)
@@ -236,7 +266,13 @@ int launch_wbfm_tc_batch(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint32_t n_cap
     p.error = ctx->d_tc_error;
     p.dbg_acc = dbg_acc;
     { const char *e = getenv("B200SDR_TC_DEBUG"); p.dbg_flags = e ? (uint32_t)atoi(e) : 0u; } /* timing experiments (tools/tc_check.py) */
-    k_wbfm_tc<<<dim3(pl.grid), B200_TC_THREADS, B200_TC_SMEM_BYTES, ctx->s_compute>>>(p);
+    /* TMA for every tile made of whole rows; the tile with a capture's ragged last row (length not a multiple of 320
+     * bytes) is filled with bounds-checked cp.async by the same kernel */
+    alignas(64) CUtensorMap tmap;
+    const bool have_map = make_tc_tensor_map(&tmap, iq_dev, n_captures, len_bytes);
+    const uint64_t whole_rows = len_bytes / B200_TC_ROW_BYTES;
+    p.manual_from_tile = !have_map ? 0u : (len_bytes % B200_TC_ROW_BYTES ? (uint32_t)(whole_rows / B200_TC_ROWS) : pl.n_tiles);
+    k_wbfm_tc<<<dim3(pl.grid), B200_TC_THREADS, B200_TC_SMEM_BYTES, ctx->s_compute>>>(p, tmap);
     CU(cudaGetLastError());
     ctx->launches += 1;
     ctx->tc_launched = true;
@@ -961,13 +997,13 @@ int32_t b200sdr_debug_wbfm_tc_acc(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint6
     DeviceGuard guard(ctx->device);
     int32_t *d_acc = nullptr;
     float *d_audio = nullptr;
-    CU(cudaMalloc((void **)&d_acc, 128 * 96 * sizeof(int32_t)));
-    CU(cudaMemset(d_acc, 0, 128 * 96 * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&d_acc, 128 * B200_TC_N * sizeof(int32_t)));
+    CU(cudaMemset(d_acc, 0, 128 * B200_TC_N * sizeof(int32_t)));
     cudaError_t e = cudaMalloc((void **)&d_audio, (b200::wbfm_audio_len(len) + 4) * sizeof(float));
     int rc = e == cudaSuccess ? launch_wbfm_tc_batch(ctx, iq_dev, 1, len, d_audio, nullptr, d_acc) : fail(ctx, B200SDR_FAIL, "cudaMalloc", e);
     if (!rc && cudaStreamSynchronize(ctx->s_compute) != cudaSuccess) rc = fail(ctx, B200SDR_FAIL, "k_wbfm_tc", cudaGetLastError());
     if (!rc) rc = check_tc_error(ctx);
-    if (!rc && cudaMemcpy(acc_host, d_acc, 128 * 96 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200SDR_FAIL;
+    if (!rc && cudaMemcpy(acc_host, d_acc, 128 * B200_TC_N * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200SDR_FAIL;
     cudaFree(d_acc);
     cudaFree(d_audio);
     if (slices_host || exponent) {

@@ -135,15 +135,17 @@ inline FmTcPlan plan_wbfm_tc(uint64_t len_bytes, uint32_t n_captures, uint32_t s
     pl.m1 = ceil_div(n, 10);
     pl.total_rows = (uint32_t)ceil_div(n, B200_TC_ROW_SAMPLES);
     pl.n_tiles = (uint32_t)ceil_div(pl.total_rows, B200_TC_ROWS);
-    /* work items = (capture, segment), handed to one persistent CTA per SM round-robin: enough items for ~8 rounds, but
-     * segments of at least 40 tiles in a batch (8 for a few captures): every segment after the first pre-rolls one tile */
-    const uint64_t want = ceil_div((uint64_t)sm_count * 8, n_captures ? n_captures : 1);
-    const uint64_t tps_min = n_captures >= 16 ? 40 : 8;
-    uint64_t tps = want ? ceil_div(pl.n_tiles, want) : pl.n_tiles;
-    if (tps < tps_min) tps = tps_min;
-    if (tps > pl.n_tiles) tps = pl.n_tiles ? pl.n_tiles : 1;
-    pl.tiles_per_segment = (uint32_t)tps;
-    pl.segments = (uint32_t)ceil_div(pl.n_tiles, tps);
+    /* work items = (capture, segment), handed to one persistent CTA per SM round-robin.  Every segment after the first
+     * pre-rolls one tile, and the CTA with the most items sets the time, so the segment length is the one that minimises
+     * rounds x (tiles per item + 1) -- at least 8 tiles, so the pre-roll stays below 1 in 9 */
+    uint64_t best_tps = pl.n_tiles ? pl.n_tiles : 1, best_cost = ~0ull;
+    for (uint64_t tps = pl.n_tiles < 8 ? (pl.n_tiles ? pl.n_tiles : 1) : 8; tps <= pl.n_tiles; ++tps) {
+        const uint64_t segs = ceil_div(pl.n_tiles, tps), rounds = ceil_div(segs * (n_captures ? n_captures : 1), sm_count);
+        const uint64_t cost = rounds * (tps + (segs > 1 ? 1 : 0));
+        if (cost < best_cost) { best_cost = cost; best_tps = tps; }
+    }
+    pl.tiles_per_segment = (uint32_t)best_tps;
+    pl.segments = (uint32_t)ceil_div(pl.n_tiles, best_tps);
     if (pl.segments == 0) pl.segments = 1;
     const uint64_t items = (uint64_t)pl.segments * n_captures;
     pl.grid = (uint32_t)(items < sm_count ? items : sm_count);
@@ -182,25 +184,28 @@ inline void fill_fm_tc(FmTcConsts &c, uint8_t *image, int8_t (*q_out)[B200_FM_T1
         c.b0_first[i] = (float)(127.5 * s0);
         c.k12_first[i] = (float)(-127.5 * (c1 * s1 + c2 * s2));
     }
-    const double alpha = deemph_alpha(), a = 1.0 - alpha, a16 = std::pow(a, B200_TC_OPR);
+    const double alpha = deemph_alpha(), a = 1.0 - alpha, a8 = std::pow(a, B200_TC_OPT), a64 = std::pow(a8, 8.0);
     c.alpha = (float)alpha;
-    for (int i = 0; i < 16; ++i) c.apow[i] = (float)std::pow(a, i + 1);
-    c.a16 = (float)a16;
-    for (int s = 0; s < 5; ++s) c.a16pow[s] = (float)std::pow(a16, double(1 << s));
-    c.a512 = (float)std::pow(a16, 32.0);
+    for (int i = 0; i < 8; ++i) c.apow[i] = (float)std::pow(a, i + 1);
+    for (int j = 0; j < 9; ++j) c.a8p[j] = (float)std::pow(a8, j);
+    c.a8 = (float)a8;
+    for (int s = 0; s < 5; ++s) c.a64pow[s] = (float)std::pow(a64, double(1 << s));
     for (int t = 0; t < B200_FM_T2; ++t) c.h2[t] = (float)h2[t];
     if (image) {
+        /* column (s, hr, j, comp) = slice s of output o = 8 hr - 1 + j of the row on the bytes of component comp; K byte
+         * 2 kap + comp is sample kap of the row's window, which starts 96 samples before the row: tap 96 + 10 o - kap */
         memset(image, 0, B200_TC_B_BYTES);
         for (int s = 0; s < 3; ++s)
-            for (int i = 0; i < B200_TC_OPR; ++i)
-                for (int comp = 0; comp < 2; ++comp) {
-                    const int n = 32 * s + 2 * i + comp;
-                    for (int kap = 0; kap < B200_TC_K_BYTES / 2; ++kap) {
-                        const int t = 80 + 10 * i - kap;
-                        if (t < 0 || t >= B200_FM_T1) continue;
-                        image[B200_TC_OP_OFF(B200_TC_N, n, 2 * kap + comp)] = (uint8_t)q[s][t];
+            for (int hr = 0; hr < 2; ++hr)
+                for (int j = 0; j <= B200_TC_OPT; ++j)
+                    for (int comp = 0; comp < 2; ++comp) {
+                        const int n = B200_TC_COL(s, hr, j, comp), o = 8 * hr - 1 + j;
+                        for (int kap = 0; kap < B200_TC_K_BYTES / 2; ++kap) {
+                            const int t = B200_TC_HIST_SAMPLES + 10 * o - kap;
+                            if (t < 0 || t >= B200_FM_T1) continue;
+                            image[B200_TC_OP_OFF(B200_TC_N, n, 2 * kap + comp)] = (uint8_t)q[s][t];
+                        }
                     }
-                }
     }
     if (q_out) memcpy(q_out, q, sizeof q);
     if (e_out) *e_out = e;

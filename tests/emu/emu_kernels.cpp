@@ -123,7 +123,7 @@ int emu_wbfm_stream(const uint8_t *iq, uint32_t n_chunks, uint64_t chunk_base, v
 }
 
 /* WBFM, tensor-core engine (csrc/wbfm_tc.cuh): the epilogue threads run on the host, the u8 x s8 -> s32 product is taken
- * from the same B image and source addressing (exact, like the hardware).  dbg_acc: optional [128][96] raw accumulators
+ * from the same B image and source addressing (exact, like the hardware).  dbg_acc: optional [128][112] raw accumulators
  * of tile 0 of capture 0; q_out: optional [3][80] tap slices; returns the tap exponent e. */
 int emu_wbfm_tc_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_bytes, uint32_t tiles_per_segment,
                       float *audio, float *disc, int32_t *dbg_acc, int8_t *q_out)
@@ -146,6 +146,7 @@ int emu_wbfm_tc_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_
     p.tiles_per_segment = pl.tiles_per_segment;
     p.segments = pl.segments;
     p.n_captures = n_captures;
+    p.manual_from_tile = 0;
     p.audio = audio;
     p.audio_stride = b200::wbfm_audio_len(len_each_bytes);
     p.disc = disc;
@@ -153,6 +154,7 @@ int emu_wbfm_tc_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_
     p.b_image = image.data();
     p.error = nullptr;
     p.dbg_acc = dbg_acc;
+    p.dbg_flags = 0;
     /* fewer CTAs than work items: every CTA walks several */
     const uint32_t items = pl.segments * n_captures;
     emu::launch(dim3(items > 2 ? 2 : items, 1), dim3(B200_TC_EPI), B200_TC_SMEM_BYTES, [&] { k_wbfm_tc(p); });
