@@ -252,9 +252,11 @@ B200_DEV bool b200_tc_src(int64_t R, int box, int chunk, uint64_t capture_bytes,
  *           half-row total -> s_tot[t & 1]
  *     ---- barrier ----
  *     C(t-1) /5 FIR of the PREVIOUS tile out of s_e[(t-1) & 1] (complete since the barrier)
- *     B(t)  every warp scans the 250 half-row totals itself, adds the carried-in part to its e[], -> s_e[t & 1]
- * so the long dependent chain of the scan runs next to the FMA stream of the previous tile's audio FIR, and nothing waits
- * on a second barrier.  acc[32 s + 2 j + c] = column B200_TC_COL(s, h, j, c) as loaded.  row = TMEM lane, h = half-row,
+ *     B1(t) every warp scans the 250 half-row totals itself -> carried-in values in its scratch   } the TMEM loads of tile
+ *     A(t+1)                                                                                     } t+1 are in flight
+ *     B2(t) adds the carried-in part to the thread's e[] -> s_e[t & 1]                            } under B1
+ * so the long dependent chain of the scan hides behind the accumulator loads and the arithmetic of the next tile, and
+ * nothing waits on a second barrier.  acc[32 s + 2 j + c] = column B200_TC_COL(s, h, j, c) as loaded.  row = TMEM lane, h = half-row,
  * et = index among the epilogue threads, ws = epilogue warp index (scratch slot). ---- */
 struct FmTcTile {
     uint32_t tile, it;
@@ -346,14 +348,14 @@ B200_DEV void b200_tc_phase_a(const FmTcParams &p, const FmTcItem &w, const FmTc
 
 /* after the tile's barrier: S[i] = a^8 S[i-1] + tot[i], S[-1] = cw (e[] just before the tile, carried in a register by
  * every thread); cin[i] = S[i-1] = e[] just before half-row i; lane l of every warp takes half-rows 8 l .. 8 l + 7 */
-B200_DEV void b200_tc_phase_b(const FmTcTile &t, float (&e)[B200_TC_OPT], int row, int h, int et, int ws, float &cw, unsigned char *smem)
+B200_DEV void b200_tc_phase_b1(const FmTcTile &t, int et, int ws, float cw, unsigned char *smem)
 {
     const FmTcConsts *k = &c_fm_tc;
     float *s_e_cur = reinterpret_cast<float *>(smem + B200_TC_SM_E) + (t.it & 1u) * B200_TC_EBUF;
     const float *s_e_prev = reinterpret_cast<const float *>(smem + B200_TC_SM_E) + ((t.it & 1u) ^ 1u) * B200_TC_EBUF;
     const float *s_tot = reinterpret_cast<const float *>(smem + B200_TC_SM_TOT) + (t.it & 1u) * 256;
     float *s_cin = reinterpret_cast<float *>(smem + B200_TC_SM_CIN) + ws * 264;
-    const int lane = et & 31, idx = 2 * row + h;
+    const int lane = et & 31;
     /* the 49 (52) newest e[] of the previous tile go in front of this tile's buffer (zeros at the start of a work item;
      * the previous tile of an item is always a full one and complete since the barrier) */
     if (et < B200_FM_HPAD) s_e_cur[et] = t.it ? s_e_prev[B200_TC_TILE_OUT + et] : 0.0f;
@@ -367,7 +369,7 @@ B200_DEV void b200_tc_phase_b(const FmTcTile &t, float (&e)[B200_TC_OPT], int ro
     }
     float v = run;
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
+    for (int s = 0; s < 3; ++s) { /* 8 lanes = 512 outputs back: what lies further has decayed by a^512 = 4e-13 */
         const float u = __shfl_up_sync(0xffffffffu, v, 1u << s);
         if (lane >= (1 << s)) v = fmaf(k->a64pow[s], u, v);
     }
@@ -385,6 +387,14 @@ B200_DEV void b200_tc_phase_b(const FmTcTile &t, float (&e)[B200_TC_OPT], int ro
     float4 *dst = reinterpret_cast<float4 *>(s_cin + 8 * lane);
     dst[0] = make_float4(c[0], c[1], c[2], c[3]);
     dst[1] = make_float4(c[4], c[5], c[6], c[7]);
+}
+/* ... second part: add the carried-in part to the thread's e[] -> s_e[t & 1] */
+B200_DEV void b200_tc_phase_b2(const FmTcTile &t, float (&e)[B200_TC_OPT], int row, int h, int ws, float &cw, unsigned char *smem)
+{
+    const FmTcConsts *k = &c_fm_tc;
+    float *s_e_cur = reinterpret_cast<float *>(smem + B200_TC_SM_E) + (t.it & 1u) * B200_TC_EBUF;
+    const float *s_cin = reinterpret_cast<const float *>(smem + B200_TC_SM_CIN) + ws * 264;
+    const int idx = 2 * row + h;
     __syncwarp();
     const float cin = s_cin[idx];
     cw = s_cin[2 * t.last + 2]; /* S[2 last + 1] = e[] after the last row that holds samples (2 last + 2 <= 250) */
@@ -474,7 +484,8 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const FmTcItem w = b200_tc_item(p, item);
         float cw = 0.0f;
-        for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it) {
+        float e_cur[B200_TC_OPT], e_next[B200_TC_OPT];
+        auto phase_a = [&](uint32_t tile, uint32_t it, float (&e)[B200_TC_OPT]) {
             const FmTcTile t = b200_tc_tile(p, w, tile, it);
             uint32_t acc[96];
             if (row < B200_TC_ROWS) b200_tc_emulated_acc(p, w, tile, row, h, acc);
@@ -483,12 +494,18 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
                 for (int s = 0; s < 3; ++s)
                     for (int jc = 0; jc < B200_TC_HALF_COLS; ++jc)
                         p.dbg_acc[row * B200_TC_N + B200_TC_SLICE_COLS * s + B200_TC_HALF_COLS * h + jc] = (int32_t)acc[32 * s + jc];
-            float e[B200_TC_OPT];
             if (tile == 0) b200_tc_phase_a<true>(p, w, t, acc, row, h, e, smem);
             else b200_tc_phase_a<false>(p, w, t, acc, row, h, e, smem);
+        };
+        if (w.t_end > w.t_begin) phase_a(w.t_begin, 0, e_cur);
+        for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it) {
+            const FmTcTile t = b200_tc_tile(p, w, tile, it);
             b200_tc_epi_sync();
             if (it) b200_tc_phase_c(p, w, b200_tc_tile(p, w, tile - 1, it - 1), tid, smem);
-            b200_tc_phase_b(t, e, row, h, tid, tid >> 5, cw, smem);
+            b200_tc_phase_b1(t, tid, tid >> 5, cw, smem);
+            if (tile + 1 < w.t_end) phase_a(tile + 1, it + 1, e_next);
+            b200_tc_phase_b2(t, e_cur, row, h, tid >> 5, cw, smem);
+            for (int i = 0; i < B200_TC_OPT; ++i) e_cur[i] = e_next[i];
         }
         if (w.t_end > w.t_begin) {
             b200_tc_epi_sync();
@@ -613,44 +630,64 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
         const int et = (warp - 2) * 32 + lane;
         uint32_t g = 0;
         bool ok = true;
+        /* accumulator columns of this thread: issue the three TMEM loads of the tile with running index g */
+        uint32_t v0[32], v1[32], v2[32];
+        auto acc_issue = [&](uint32_t gi) -> bool {
+            const uint32_t stage = gi & 1u, phase = (gi >> 1) & 1u;
+            if (!b200_tc_wait(bar_tfull + stage, phase, s_abort)) return false;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + stage * B200_TC_ACC_COLS + B200_TC_HALF_COLS * h;
+            b200_tc_ld32(taddr, v0);
+            b200_tc_ld32(taddr + B200_TC_SLICE_COLS, v1);
+            b200_tc_ld32(taddr + 2 * B200_TC_SLICE_COLS, v2);
+            return true;
+        };
+        /* ... wait for them, release the accumulator stage, run phase A */
+        auto acc_use = [&](const FmTcItem &w, uint32_t gi, uint32_t tile, uint32_t it, float (&e)[B200_TC_OPT]) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint32_t acc[96];
+#pragma unroll
+            for (int n = 0; n < 32; ++n) { acc[n] = v0[n]; acc[32 + n] = v1[n]; acc[64 + n] = v2[n]; }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) b200_tc_arrive(bar_tempty + (gi & 1u)); /* the MMA warp may overwrite this accumulator */
+            if (p.dbg_acc && w.capture == 0 && tile == 0) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+#pragma unroll
+                    for (int jc = 0; jc < B200_TC_HALF_COLS; ++jc)
+                        p.dbg_acc[row * B200_TC_N + B200_TC_SLICE_COLS * s + B200_TC_HALF_COLS * h + jc] = (int32_t)acc[32 * s + jc];
+            }
+            if (p.dbg_flags & 2u) return;
+            const FmTcTile t = b200_tc_tile(p, w, tile, it);
+            if (tile == 0) b200_tc_phase_a<true>(p, w, t, acc, row, h, e, smem);
+            else b200_tc_phase_a<false>(p, w, t, acc, row, h, e, smem);
+        };
         for (uint32_t item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
             const FmTcItem w = b200_tc_item(p, item);
+            if (w.t_end <= w.t_begin) continue;
             float cw = 0.0f;
-            for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it, ++g) {
-                const uint32_t stage = g & 1u, phase = (g >> 1) & 1u;
-                if (!b200_tc_wait(bar_tfull + stage, phase, s_abort)) { ok = false; break; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t acc[96];
-                {
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + stage * B200_TC_ACC_COLS + B200_TC_HALF_COLS * h;
-                    uint32_t v0[32], v1[32], v2[32];
-                    b200_tc_ld32(taddr, v0);
-                    b200_tc_ld32(taddr + B200_TC_SLICE_COLS, v1);
-                    b200_tc_ld32(taddr + 2 * B200_TC_SLICE_COLS, v2);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int n = 0; n < 32; ++n) { acc[n] = v0[n]; acc[32 + n] = v1[n]; acc[64 + n] = v2[n]; }
+            float e_cur[B200_TC_OPT], e_next[B200_TC_OPT];
+            if (!acc_issue(g)) { ok = false; break; }
+            acc_use(w, g, w.t_begin, 0, e_cur);
+            ++g;
+            for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it) {
+                const bool more = tile + 1 < w.t_end;
+                if (p.dbg_flags & 2u) { /* timing experiment: accumulator traffic only */
+                    if (more) { if (!acc_issue(g)) { ok = false; break; } acc_use(w, g, tile + 1, it + 1, e_next); ++g; }
+                    continue;
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) b200_tc_arrive(bar_tempty + stage); /* the MMA warp may overwrite this accumulator */
-                if (p.dbg_acc && w.capture == 0 && tile == 0) {
-#pragma unroll
-                    for (int s = 0; s < 3; ++s)
-#pragma unroll
-                        for (int jc = 0; jc < B200_TC_HALF_COLS; ++jc)
-                            p.dbg_acc[row * B200_TC_N + B200_TC_SLICE_COLS * s + B200_TC_HALF_COLS * h + jc] = (int32_t)acc[32 * s + jc];
-                }
-                if (p.dbg_flags & 2u) continue;
                 const FmTcTile t = b200_tc_tile(p, w, tile, it);
-                float e[B200_TC_OPT];
-                if (tile == 0) b200_tc_phase_a<true>(p, w, t, acc, row, h, e, smem);
-                else b200_tc_phase_a<false>(p, w, t, acc, row, h, e, smem);
                 b200_tc_epi_sync();
                 if (it) b200_tc_phase_c(p, w, b200_tc_tile(p, w, tile - 1, it - 1), et, smem);
-                b200_tc_phase_b(t, e, row, h, et, warp - 2, cw, smem);
+                if (more && !acc_issue(g)) { ok = false; break; } /* the next tile's accumulators are on their way ... */
+                b200_tc_phase_b1(t, et, warp - 2, cw, smem);        /* ... under the scan of this tile's totals        */
+                if (more) { acc_use(w, g, tile + 1, it + 1, e_next); ++g; }
+                b200_tc_phase_b2(t, e_cur, row, h, warp - 2, cw, smem);
+#pragma unroll
+                for (int i = 0; i < B200_TC_OPT; ++i) e_cur[i] = e_next[i];
             }
-            if (ok && !(p.dbg_flags & 2u) && w.t_end > w.t_begin) { /* drain: the audio of the item's last tile */
+            if (ok && !(p.dbg_flags & 2u)) { /* drain: the audio of the item's last tile */
                 b200_tc_epi_sync();
                 b200_tc_phase_c(p, w, b200_tc_tile(p, w, w.t_end - 1, w.t_end - 1 - w.t_begin), et, smem);
             }
