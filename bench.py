@@ -91,12 +91,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(B, world):
+def workload_config(B, world, fir_engine="tensor"):
     """The `config` object of BOTH arms (the GPU arm runs it whole; the CPU arm runs a bounded sample of it)."""
     return {"workload": "configs[4] per-GPU share (= configs[1] spectrum + configs[2] WBFM on every capture): "
                         f"{B} x 10 s captures (48 MB u8 I/Q each) per GPU, both chains per step",
             "captures_per_gpu": B, "capture_seconds": 10, "sample_rate": 2.4e6, "nfft": 1024, "hop": 512,
-            "window": "hann", "cache": f"inputs {B * CAPTURE_BYTES / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
+            "window": "hann", "fir_engine": fir_engine,
+            "cache": f"inputs {B * CAPTURE_BYTES / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
             "parallelism": f"captures sharded over {world} GPU(s), no collective"}
 
 
@@ -196,7 +197,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.captures_per_gpu, world),
+            "config": workload_config(args.captures_per_gpu, world, args.fir_engine),
             "cpu_baseline": res, "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -302,6 +303,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-captures", type=int, default=64, help="captures per rank recomputed one at a time (bitwise check)")
     ap.add_argument("--config4-waves", type=int, default=8, help="N=1 only: waves of captures-per-gpu captures (8 x 512 = configs[4]); 0 = skip")
+    ap.add_argument("--fir-engine", default="tensor", choices=["tensor", "fp32"],
+                    help="stage-1 FIR engine of the batched WBFM chain the step (and e2e) runs: tensor = exact u8 x s8 tcgen05 product "
+                         "(csrc/wbfm_tc.cuh), fp32 = CUDA-core scatter FIR (csrc/wbfm.cuh); the other engine is timed beside it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -336,7 +340,10 @@ def main():
     importlib.import_module("stm32f7-rtlsdr_b200.build").build()
     pkg = importlib.import_module("stm32f7-rtlsdr_b200")
     sharding = importlib.import_module("stm32f7-rtlsdr_b200.sharding")
-    sdr = pkg.B200Sdr(device=local_rank, chains=pkg.CHAIN_SPECTRUM | pkg.CHAIN_WBFM)
+    engines = {"tensor": pkg.FIR_ENGINE_TENSOR, "fp32": pkg.FIR_ENGINE_FP32}
+    other_engine = "fp32" if args.fir_engine == "tensor" else "tensor"
+    sdr = pkg.B200Sdr(device=local_rank, chains=pkg.CHAIN_SPECTRUM | pkg.CHAIN_WBFM, fir_engine=engines[args.fir_engine])
+    sdr_other = pkg.B200Sdr(device=local_rank, chains=pkg.CHAIN_WBFM, fir_engine=engines[other_engine])  # timed beside it
 
     B = args.captures_per_gpu
     lo, hi = sharding.shard_range(B * world, rank, world)   # this rank's captures of the whole job
@@ -384,6 +391,23 @@ def main():
     launches = sdr.kernel_launches() - l0
     ms_spec = timed(1, args.steps)
     ms_fm = timed(2, args.steps)
+    # the same WBFM batch through the OTHER stage-1 FIR engine (own context, own stream), and how far its audio is from
+    # the step's engine (both are within the parity tolerance of the float64 golden model; tests/test_gpu_parity.py)
+    audio_other = torch.empty(B * n_audio, dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        sdr_other.batch_wbfm_dev(iq.data_ptr(), B, CAPTURE_BYTES, audio_other.data_ptr())
+    sdr_other.sync()
+    barrier()
+    sdr_other.timer_start()
+    for _ in range(args.steps):
+        sdr_other.batch_wbfm_dev(iq.data_ptr(), B, CAPTURE_BYTES, audio_other.data_ptr())
+    ms_fm_other = max_over_ranks(sdr_other.timer_stop_ms())
+    sdr_other.sync()
+    n_cmp = min(B, 64) * n_audio
+    engines_max_diff = float((audio_other[:n_cmp] - audio[:n_cmp]).abs().max())
+    sys.stderr.write(f"engines: max |audio| {float(audio[:n_cmp].abs().max()):.6f} / {float(audio_other[:n_cmp].abs().max()):.6f}, "
+                     f"max difference {engines_max_diff:.3e}\n")
+    del audio_other
     clocks = sampler.stop()
     step(4)
     sdr.sync()
@@ -432,6 +456,7 @@ def main():
     spec_gbs = 2.0 * B * CAPTURE_SAMPLES * args.steps / (ms_spec * 1e-3) / 1e9            # per GPU
     fm_bytes = 2.0 + 4.0 * 48000.0 / 2400000.0
     fm_gbs = fm_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_fm * 1e-3) / 1e9
+    fm_other_gbs = fm_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_fm_other * 1e-3) / 1e9
     am_bytes = 2.0 + 4.0 * 8000.0 / 2400000.0
     am_gbs = am_bytes * B * CAPTURE_SAMPLES * args.steps / (ms_am * 1e-3) / 1e9
 
@@ -614,7 +639,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, world),
+            "config": workload_config(B, world, args.fir_engine),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "MS/s", "h2d_bytes_per_step": E * CAPTURE_BYTES,
                     "d2h_bytes_per_step": E * (1024 + n_audio) * 4, "captures_per_step": E, "steps": e2e_steps,
@@ -639,7 +664,14 @@ def main():
                              "GBps": spec_gbs, "hbm_frac": spec_gbs / hbm_peak, "hbm_frac_nominal_8TBps": spec_gbs / 8000.0},
                 "wbfm": {"ms_per_step": ms_fm / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_fm * 1e-3) / 1e6,
                          "GBps": fm_gbs, "hbm_frac": fm_gbs / hbm_peak, "hbm_frac_nominal_8TBps": fm_gbs / 8000.0,
-                         "algorithmic_bytes_per_sample": fm_bytes},
+                         "algorithmic_bytes_per_sample": fm_bytes, "fir_engine": args.fir_engine,
+                         "kernel": "k_wbfm_tc" if args.fir_engine == "tensor" else "k_wbfm"},
+                "wbfm_" + other_engine + "_engine": {
+                    "ms_per_step": ms_fm_other / args.steps, "MSps_per_gpu": B * CAPTURE_SAMPLES * args.steps / (ms_fm_other * 1e-3) / 1e6,
+                    "GBps": fm_other_gbs, "hbm_frac": fm_other_gbs / hbm_peak, "hbm_frac_nominal_8TBps": fm_other_gbs / 8000.0,
+                    "algorithmic_bytes_per_sample": fm_bytes, "kernel": "k_wbfm_tc" if other_engine == "tensor" else "k_wbfm",
+                    "max_abs_audio_difference_between_engines": engines_max_diff,
+                    "note": "the same batch through the other stage-1 FIR engine (cfg.fir_engine); not part of `value`"},
                 "convert_cf32": {"ms_per_step": ms_conv / args.steps, "MSps_per_gpu": Bc * CAPTURE_SAMPLES * args.steps / (ms_conv * 1e-3) / 1e6,
                                  "GBps": conv_gbs, "hbm_frac": conv_gbs / hbm_peak, "algorithmic_bytes_per_sample": 10.0,
                                  "note": "K2 alone over %d captures: HBM-bound reference, not part of `value`" % Bc},
@@ -662,6 +694,7 @@ def main():
         if split is not None:
             line["split_capture"] = split
         print(json.dumps(line))
+    sdr_other.close()
     sdr.close()
     if world > 1:
         dist.barrier()   # rank 0 also ran the ingest probe; leave together

@@ -219,6 +219,92 @@ def test_wbfm_host_path_equals_device_path(sdr, g):
     assert np.array_equal(a_host, a_dev)
 
 
+# ------------------------------------------------------------- WBFM, tensor-core FIR engine (K4-FM-TC)
+@pytest.fixture(scope="module")
+def sdr_tc(sdr_lib):
+    s = sdr_lib.B200Sdr(fir_engine=sdr_lib.FIR_ENGINE_TENSOR)
+    yield s
+    s.close()
+
+
+def test_tensor_engine_accumulators_bit_exact(sdr_tc, g):
+    """csrc/wbfm_tc.cuh: the tcgen05.mma kind::i8 product of the raw bytes (TMA-loaded, 64B swizzle) with the three signed
+    8-bit tap slices is an integer FIR; its first tile must equal numpy's integer convolution bit for bit (this pins the
+    tensor map, both shared-memory operand layouts, the descriptors and the accumulator addressing)."""
+    n = 160 * 125 * 2 + 1232
+    iq = g.synth(1, 2 * n, SYNTH_WBFM, 11)
+    acc, q, e = sdr_tc.debug_wbfm_tc_acc(iq)
+    h = g.taps(0)
+    hq = (q[0] * 2.0**-7 + q[1] * 2.0**-14 + q[2] * 2.0**-21) / 2.0**e
+    assert np.max(np.abs(hq - h)) < 4e-7 * np.max(np.abs(h))                # the slices ARE the oracle's taps to 21 bits
+    u = iq.astype(np.int64)
+    for s_ in range(3):
+        for c in (0, 1):
+            x = np.concatenate([np.zeros(96, np.int64), u[c::2]])           # x[n < 0] = 0
+            full = np.convolve(x, q[s_].astype(np.int64))                    # full[96 + n] = sum_t q[t] x[n - t]
+            for hr in (0, 1):
+                for j in range(9):                                           # output m = 16 r + 8 hr - 1 + j, sample 10 m
+                    m = 16 * np.arange(125) + 8 * hr - 1 + j
+                    assert np.array_equal(acc[:125, 36 * s_ + 18 * hr + 2 * j + c], full[96 + 10 * m]), (s_, c, hr, j)
+
+
+@pytest.mark.parametrize("n_captures,len_each", [(1, 16), (1, 2416), (2, 262144), (3, 30720 * 5 + 240 * 3 + 16), (1, 4800000),
+                                                 (2, 320 * 125 * 3), (5, 320 * 130 + 16), (1, 320)])
+def test_tensor_engine_batches(sdr_tc, g, n_captures, len_each):
+    """same cases as test_wbfm_batches plus lengths that are / are not whole 320-byte rows (TMA tiles vs the
+    bounds-checked cp.async fill of a capture's ragged last tile) and several captures per CTA"""
+    iq = g.synth(n_captures, len_each, SYNTH_WBFM, 50)
+    audio, disc = sdr_tc.wbfm(iq, n_captures, want_disc=True)
+    for c in range(n_captures):
+        ga, gd = g.wbfm(iq[c * len_each:(c + 1) * len_each], want_disc=True)
+        assert audio[c].size == ga.size and disc[c].size == gd.size
+        assert np.max(np.abs(wrap_phase(disc[c] - gd))) <= DISC_ATOL
+        assert np.max(np.abs(audio[c] - ga)) <= FM_AUDIO_ATOL
+
+
+def test_tensor_engine_golden_fixture_and_engines_agree(sdr, sdr_tc, sdr_lib, vec, g):
+    iq = sdr_lib.synth_fill_host(1, int(vec["fm_len"]), SYNTH_WBFM, int(vec["fm_seed"]))
+    audio, disc = sdr_tc.wbfm(iq, want_disc=True)
+    assert np.max(np.abs(wrap_phase(disc[0] - vec["fm_disc"]))) <= DISC_ATOL
+    assert np.max(np.abs(audio[0] - vec["fm_audio"])) <= FM_AUDIO_ATOL
+    a32, d32 = sdr.wbfm(iq, want_disc=True)
+    assert 0 < np.max(np.abs(audio - a32)) <= 2e-6 and np.max(np.abs(wrap_phase(disc[0] - d32[0]))[8:]) <= 5e-6
+    # the host-buffer path (b200sdr_batch_host) runs the same engine
+    iq4 = g.synth(4, 262144, SYNTH_WBFM, 60)
+    assert np.array_equal(sdr_tc.wbfm(iq4, 4), sdr_tc.wbfm(iq4, 4, want_disc=True)[0])
+
+
+@pytest.mark.parametrize("name", ["fullscale_tone", "half_lsb_rotation", "tone_on_dc"])
+def test_tensor_engine_extreme_bytes(sdr_tc, g, name):
+    """the offset is removed in exact integer / half-integer arithmetic: even the smallest phasor a u8 stream can
+    carry stays far inside the bound (3e-7 rad measured, 6.5e-5 for the FP32 engine)"""
+    nb = 2 * (30720 * 3 + 1208)
+    iq = extreme_patterns(nb)[1][name]
+    audio, disc = sdr_tc.wbfm(iq, 1, want_disc=True)
+    ga, gd = g.wbfm(iq, want_disc=True)
+    assert np.max(np.abs(wrap_phase(disc[0] - gd))[16:]) <= 2e-5
+    assert np.max(np.abs(audio[0] - ga)[8:]) <= 2e-5
+
+
+def test_tensor_engine_full_size_capture_alone_equals_in_batch(sdr_tc, g):
+    """a 10 s capture (1200 tiles, many segments with pre-roll) against the oracle, and bitwise the same audio alone
+    and inside a batch that changes the segment plan"""
+    len_each = 48_000_000
+    iq = g.synth(1, len_each, SYNTH_WBFM, 1001)
+    alone, disc = sdr_tc.wbfm(iq, 1, want_disc=True)
+    ga, gd = g.wbfm(iq, want_disc=True)
+    assert np.max(np.abs(alone[0] - ga)) <= FM_AUDIO_ATOL and np.max(np.abs(wrap_phase(disc[0] - gd))) <= DISC_ATOL
+    both = sdr_tc.wbfm(np.concatenate([g.synth(1, len_each, SYNTH_WBFM, 7), iq]), 2)
+    # segments after the first pre-roll one tile (de-emphasis pole 0.946^2000 = 0): the plan changes where they start
+    assert np.max(np.abs(both[1] - alone[0])) <= 1e-6
+
+
+def test_fir_engine_config_is_validated(sdr_lib):
+    with pytest.raises(sdr_lib.B200SdrError) as ei:
+        sdr_lib.B200Sdr(fir_engine=2)
+    assert ei.value.status == sdr_lib.NOT_SUPPORTED
+
+
 # ------------------------------------------------------------------------- test-mode counter (K0)
 @pytest.mark.parametrize("nbytes", [0, 4, 12, 16, 20, 1020, 16384 + 8, 262144, 4 * 262144 + 4])
 def test_counter_check_host_blocks(sdr, g, nbytes):
