@@ -333,10 +333,23 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         __syncthreads();
         if (s_cvt[3]) {
             __threadfence();
-            for (int k = tid; k < 1024; k += B200_SPEC_THREADS) {
-                float sum = 0.0f;
-                for (uint32_t i = 0; i < p.total_units; ++i) sum += __ldcg(p.partials + (uint64_t)i * 1024u + k);
-                float r = sum * p.final_scale;
+            /* a thread owns the bins tid + THREADS j; per bin the units are added in order (the same sum as the separate
+             * kernel, bit for bit), and the loads of all its bins and of four units at a time are in flight together --
+             * one CTA does this alone, so it is the latency of the loads that counts */
+            constexpr int NB = 1024 / B200_SPEC_THREADS;
+            float sum[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) sum[j] = 0.0f;
+#pragma unroll 4
+            for (uint32_t i = 0; i < p.total_units; ++i) {
+                const float *src = p.partials + (uint64_t)i * 1024u + tid;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) sum[j] += __ldcg(src + j * B200_SPEC_THREADS);
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int k = tid + j * B200_SPEC_THREADS;
+                float r = sum[j] * p.final_scale;
                 if (p.carry) r = fmaf(p.carry[k], p.carry_scale, r);
                 p.final_out[k] = r;
             }
