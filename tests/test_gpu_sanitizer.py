@@ -41,6 +41,13 @@ SCRIPT = textwrap.dedent("""
         for off in range(0, 4 * 4100, 4100):
             c.process_samples(cnt[off:off + 4100])
         assert c.get_counter_check()[0] == 2
+    # tensor-core FIR engine (csrc/wbfm_tc.cuh): two full tiles through the TMA tensor map + a ragged one through the
+    # bounds-checked cp.async fill per capture, mbarrier pipeline, tcgen05.mma / tcgen05.ld, named barrier of the epilogue
+    iq2 = pkg.synth_fill_host(2, 40000 * 2 + 4800, pkg.SYNTH_WBFM, 3)
+    with pkg.B200Sdr(chains=pkg.CHAIN_WBFM, fir_engine=pkg.FIR_ENGINE_TENSOR) as t:
+        a = t.wbfm(iq2, 2)
+        b, d = t.wbfm(iq2, 2, want_disc=True)
+        assert np.array_equal(a, b) and np.isfinite(d).all()
     print("SANITIZED_RUN_OK")
 """) % ROOT
 
