@@ -249,7 +249,7 @@ def test_tensor_engine_accumulators_bit_exact(sdr_tc, g):
 
 
 @pytest.mark.parametrize("n_captures,len_each", [(1, 16), (1, 2416), (2, 262144), (3, 30720 * 5 + 240 * 3 + 16), (1, 4800000),
-                                                 (2, 320 * 125 * 3), (5, 320 * 130 + 16), (1, 320)])
+                                                 (2, 320 * 125 * 3), (5, 320 * 130 + 16), (1, 320), (300, 4096), (40, 3200)])
 def test_tensor_engine_batches(sdr_tc, g, n_captures, len_each):
     """same cases as test_wbfm_batches plus lengths that are / are not whole 320-byte rows (TMA tiles vs the
     bounds-checked cp.async fill of a capture's ragged last tile) and several captures per CTA"""
