@@ -27,8 +27,8 @@
  *               the rows behind its end are out of bounds = zero-filled by the hardware.  A capture whose length is
  *               not a multiple of 320 bytes has its last tile filled by the whole warp with bounds-checked cp.async
  *               instead (same layout);
- *   warp 1      one lane issues the 16 tcgen05.mma per tile into one of two TMEM accumulator stages and commits to the
- *               "stage free" and "accumulator full" mbarriers;
+ *   warp 1      one lane issues the 16 tcgen05.mma per tile into one of two TMEM accumulator stages and commits ONCE to the
+ *               tile's "MMAs done" mbarrier, which both frees the operand stage and hands the accumulator on;
  *   warps 2..9  epilogue on half-rows: warp w reads TMEM lanes 32 (w % 4) .., columns of half-row (w - 2) / 4; a thread
  *               removes the 127.5 offset from the leading slice exactly (an integer and a half-integer below 2^23 are
  *               exact floats), adds the two small slices, and runs the 240 kS/s stages on its 8 consecutive outputs:
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
             const uint8_t *cap = p.iq + (uint64_t)w.capture * p.capture_stride;
             for (uint32_t tile = w.t_begin; tile < w.t_end; ++tile, ++g) {
                 const uint32_t stage = g & 1u, phase = (g >> 1) & 1u;
-                if (!b200_tc_wait(bar_empty + stage, phase ^ 1u, s_abort)) { ok = false; break; }
+                if (!b200_tc_wait(bar_tfull + stage, phase ^ 1u, s_abort)) { ok = false; break; } /* MMAs of the tile two back done */
                 const uint32_t a_stage = a_base + stage * B200_TC_A_STAGE;
                 const int32_t R0 = (int32_t)(tile * B200_TC_ROWS);
                 if (p.dbg_flags & 1u) {
@@ -615,8 +615,9 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
                         const uint64_t db = b200_tc_desc(b_base + (uint32_t)((ks >> 1) * B200_TC_B_BOX + (ks & 1) * 32));
                         b200_tc_mma(tmem + stage * B200_TC_ACC_COLS, da, db, ks > 0 ? 1u : 0u);
                     }
-                    b200_tc_commit(bar_empty + stage);  /* the operand stage is free once the MMAs have read it */
-                    b200_tc_commit(bar_tfull + stage);  /* ... and the accumulator is complete                  */
+                    /* ONE commit per tile (each costs the tensor pipe a drain, profiles/r2_wbfm_tc.txt): the same event frees
+                     * the operand stage for the producer and hands the accumulator to the epilogue */
+                    b200_tc_commit(bar_tfull + stage);
                 }
             }
             if (fail) { *s_abort = 1u; atomicCAS(p.error, 0u, fail); }
