@@ -273,6 +273,9 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __ldg(const float *p) { return *p; }
 static inline float __ldcg(const float *p) { return *p; }
+static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
+static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
+static inline int __float2int_rn(float f) { return (int)nearbyintf(f); }
 static inline unsigned __ldg(const unsigned *p) { return *p; }
 static inline unsigned short __ldg(const unsigned short *p) { return *p; }
 static inline uint4 __ldg(const uint4 *p) { return *p; }
