@@ -333,22 +333,23 @@ __global__ void __launch_bounds__(B200_SPEC_THREADS, B200_SPEC_MINB) k_spectrum(
         __syncthreads();
         if (s_cvt[3]) {
             __threadfence();
-            /* a thread owns the bins tid + THREADS j; per bin the units are added in order (the same sum as the separate
-             * kernel, bit for bit), and the loads of all its bins and of four units at a time are in flight together --
-             * one CTA does this alone, so it is the latency of the loads that counts */
-            constexpr int NB = 1024 / B200_SPEC_THREADS;
-            float sum[NB];
+            /* a thread owns the bins 4 tid .. 4 tid + 3 and 512 + 4 tid ..; per bin the units are added in order (the same
+             * sum as the separate kernel, bit for bit), with 128-bit loads and eight units at a time in flight -- one CTA
+             * does this alone, so it is the latency of the loads that counts */
+            static_assert(B200_SPEC_THREADS == 128, "folded finalize: 128 threads x 2 x float4 = 1024 bins");
+            float sum[8];
 #pragma unroll
-            for (int j = 0; j < NB; ++j) sum[j] = 0.0f;
-#pragma unroll 4
+            for (int j = 0; j < 8; ++j) sum[j] = 0.0f;
+#pragma unroll 8
             for (uint32_t i = 0; i < p.total_units; ++i) {
-                const float *src = p.partials + (uint64_t)i * 1024u + tid;
-#pragma unroll
-                for (int j = 0; j < NB; ++j) sum[j] += __ldcg(src + j * B200_SPEC_THREADS);
+                const float4 *src = reinterpret_cast<const float4 *>(p.partials + (uint64_t)i * 1024u) + tid;
+                const float4 a = __ldcg(src), c = __ldcg(src + 128);
+                sum[0] += a.x; sum[1] += a.y; sum[2] += a.z; sum[3] += a.w;
+                sum[4] += c.x; sum[5] += c.y; sum[6] += c.z; sum[7] += c.w;
             }
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const int k = tid + j * B200_SPEC_THREADS;
+            for (int j = 0; j < 8; ++j) {
+                const int k = (j < 4 ? 0 : 512) + 4 * tid + (j & 3);
                 float r = sum[j] * p.final_scale;
                 if (p.carry) r = fmaf(p.carry[k], p.carry_scale, r);
                 p.final_out[k] = r;

@@ -273,6 +273,7 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __ldg(const float *p) { return *p; }
 static inline float __ldcg(const float *p) { return *p; }
+static inline float4 __ldcg(const float4 *p) { return *p; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 static inline int __float2int_rn(float f) { return (int)nearbyintf(f); }
