@@ -279,9 +279,10 @@ B200SDR_API int32_t b200sdr_get_taps(b200sdr_ctx *ctx, uint32_t which, float *ou
 B200SDR_API int32_t b200sdr_get_window(b200sdr_ctx *ctx, uint32_t window, float *out1024);
 
 /* Parity hook of the TENSOR FIR engine: run it over ONE device-resident capture (len % 16 == 0) and return the raw
- * 32-bit accumulators of its first tile, acc_host[row r][36 s + 18 h + 2 j + c] = sum_t q_s[t] u[2 (10 m - t) + c] with
- * m = 16 r + 8 h - 1 + j (128 x 112: slice s = 0..2, half-row h = 0..1, j = 0..8, component c; rows 125..127 and columns
- * 108..111 unused; u[n < 0] = 0), the three signed 8-bit tap slices (slices_host[3][80], may be NULL) and the
+ * 32-bit accumulators of its first tile, acc_host[row r][34 s + 2 j + c] = sum_t q_s[t] u[2 (10 m - t) + c] with
+ * m = 16 r - 1 + j (128 x 112: slice s = 0..2, j = 0..16 -- the output before the row, then its sixteen --, component c;
+ * rows 125..127 and columns 102..111 unused; u[n < 0] = 0), the three signed 8-bit tap slices (slices_host[3][80], may be
+ * NULL) and the
  * exponent e with h[t] 2^e = q0 2^-7 + q1 2^-14 + q2 2^-21 (may be NULL): the integer product must be bit-exact. */
 B200SDR_API int32_t b200sdr_debug_wbfm_tc_acc(b200sdr_ctx *ctx, const uint8_t *iq_dev, uint64_t len, int32_t *acc_host,
                                               int8_t *slices_host, int32_t *exponent);

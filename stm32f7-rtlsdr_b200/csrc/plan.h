@@ -184,28 +184,25 @@ inline void fill_fm_tc(FmTcConsts &c, uint8_t *image, int8_t (*q_out)[B200_FM_T1
         c.b0_first[i] = (float)(127.5 * s0);
         c.k12_first[i] = (float)(-127.5 * (c1 * s1 + c2 * s2));
     }
-    const double alpha = deemph_alpha(), a = 1.0 - alpha, a8 = std::pow(a, B200_TC_OPT), a64 = std::pow(a8, 8.0);
+    const double alpha = deemph_alpha(), a = 1.0 - alpha, a16 = std::pow(a, B200_TC_OPR);
     c.alpha = (float)alpha;
-    for (int i = 0; i < 8; ++i) c.apow[i] = (float)std::pow(a, i + 1);
-    for (int j = 0; j < 9; ++j) c.a8p[j] = (float)std::pow(a8, j);
-    c.a8 = (float)a8;
-    for (int s = 0; s < 5; ++s) c.a64pow[s] = (float)std::pow(a64, double(1 << s));
+    for (int i = 0; i < B200_TC_OPR; ++i) c.apow[i] = (float)std::pow(a, i + 1);
+    for (int s = 0; s < 5; ++s) c.a16pow[s] = (float)std::pow(a16, double(1 << s));
     for (int t = 0; t < B200_FM_T2; ++t) c.h2[t] = (float)h2[t];
     if (image) {
-        /* column (s, hr, j, comp) = slice s of output o = 8 hr - 1 + j of the row on the bytes of component comp; K byte
-         * 2 kap + comp is sample kap of the row's window, which starts 96 samples before the row: tap 96 + 10 o - kap */
+        /* column (s, j, comp) = slice s of output o = j - 1 of the row on the bytes of component comp; K byte 2 kap + comp is
+         * sample kap of the row's window, which starts 96 samples before the row: tap 96 + 10 o - kap */
         memset(image, 0, B200_TC_B_BYTES);
         for (int s = 0; s < 3; ++s)
-            for (int hr = 0; hr < 2; ++hr)
-                for (int j = 0; j <= B200_TC_OPT; ++j)
-                    for (int comp = 0; comp < 2; ++comp) {
-                        const int n = B200_TC_COL(s, hr, j, comp), o = 8 * hr - 1 + j;
-                        for (int kap = 0; kap < B200_TC_K_BYTES / 2; ++kap) {
-                            const int t = B200_TC_HIST_SAMPLES + 10 * o - kap;
-                            if (t < 0 || t >= B200_FM_T1) continue;
-                            image[B200_TC_OP_OFF(B200_TC_N, n, 2 * kap + comp)] = (uint8_t)q[s][t];
-                        }
+            for (int j = 0; j <= B200_TC_OPR; ++j)
+                for (int comp = 0; comp < 2; ++comp) {
+                    const int n = B200_TC_COL(s, j, comp), o = j - 1;
+                    for (int kap = 0; kap < B200_TC_K_BYTES / 2; ++kap) {
+                        const int t = B200_TC_HIST_SAMPLES + 10 * o - kap;
+                        if (t < 0 || t >= B200_FM_T1) continue;
+                        image[B200_TC_OP_OFF(B200_TC_N, n, 2 * kap + comp)] = (uint8_t)q[s][t];
                     }
+                }
     }
     if (q_out) memcpy(q_out, q, sizeof q);
     if (e_out) *e_out = e;

@@ -12,15 +12,15 @@
  * 512 raw bytes: 192 bytes (96 samples) of history, [320 R - 192, 320 R), then the row's own 320 bytes -- unsigned
  * 8-bit, interleaved I,Q exactly as the dongle delivers them, no conversion, no de-interleave.  The row yields the 16
  * stage-1 outputs y1[16 R + o], o = 0..15, and once more the output before them (o = -1), so the discriminator of a row
- * needs nothing from its neighbour.  The B operand is constant: column (s, h, j, c) holds slice s of the taps of output
- * o = 8 h - 1 + j (half-row h = 0, 1; j = 0..8) on the bytes of component c (I or Q), zero on the other component:
- *     B[(s, h, j, c)][2 kap + c'] = (c' == c) ? q_s[96 + 10 o - kap] : 0             (tap index 0..79, else 0)
+ * needs nothing from its neighbour.  The B operand is constant: column (s, j, c) holds slice s of the taps of output
+ * o = j - 1 (j = 0..16) on the bytes of component c (I or Q), zero on the other component:
+ *     B[(s, j, c)][2 kap + c'] = (c' == c) ? q_s[96 + 10 o - kap] : 0                (tap index 0..79, else 0)
  * where the float64-designed taps are cut into three signed 8-bit slices, h[t] 2^e = q0 2^-7 + q1 2^-14 + q2 2^-21
  * (21 bits + sign: 3.6e-7 of the largest tap).  D = A B is u8 x s8 -> s32, exact.  One tile = 125 rows (M = 128 with
  * three idle rows: 125 x 16 = 2000 outputs = 400 audio samples, so every tile starts on an audio sample), N = 112
- * (108 used), K = 512 = 16 MMAs of K = 32.
+ * (102 used), K = 512 = 16 MMAs of K = 32.
  *
- * Roles (one CTA of 320 threads per SM, persistent over (capture, segment) work items):
+ * Roles (one CTA of 320 threads per SM, persistent over (capture, segment) work items whose tiles it walks in order):
  *   warp 0      producer: ONE lane issues 8 TMA tensor copies per tile (cp.async.bulk.tensor, 64B swizzle: three
  *               64-byte columns of history from row R - 1, five of the row itself) into one of two operand stages; the
  *               tensor map is the plain (320 bytes, rows, captures) view of the batch, so the row before a capture and
@@ -29,17 +29,21 @@
  *               instead (same layout);
  *   warp 1      one lane issues the 16 tcgen05.mma per tile into one of two TMEM accumulator stages and commits ONCE to the
  *               tile's "MMAs done" mbarrier, which both frees the operand stage and hands the accumulator on;
- *   warps 2..9  epilogue on half-rows: warp w reads TMEM lanes 32 (w % 4) .., columns of half-row (w - 2) / 4; a thread
- *               removes the 127.5 offset from the leading slice exactly (an integer and a half-integer below 2^23 are
- *               exact floats), adds the two small slices, and runs the 240 kS/s stages on its 8 consecutive outputs:
- *               discriminator, de-emphasis as a scan (thread-serial, then every warp scans the 250 half-row totals
- *               itself), /5 FIR out of a double-buffered shared window, software-pipelined: ONE CTA-wide (256-thread)
- *               barrier per tile, the scan of tile t runs next to the audio FIR of tile t-1.  The MMAs of tile t+1 run
- *               while tile t is in the epilogue.
+ *   warps 2..5 / 6..9   two epilogue GROUPS that take the tiles in turn (group = accumulator stage = tile index mod 2).
+ *               Warp w reads TMEM lanes 32 (w % 4) .., a thread owns a ROW: it removes the 127.5 offset from the leading
+ *               slice exactly (an integer and a half-integer below 2^23 are exact floats), adds the two small slices, and
+ *               runs the 240 kS/s stages on its 16 consecutive outputs: discriminator, de-emphasis as a scan (thread-serial,
+ *               then shuffle scans over the warp's 32 rows and the 32 rows before them -- what lies further back has
+ *               decayed by a^512 = 4e-13 --, no shared-memory round trip), /5 FIR out of a shared window.  A group meets
+ *               at its own 128-thread barrier once per tile; what a tile needs from the tile before it (the other group's:
+ *               row totals, the newest 49 e[]) is ordered by a counter the groups bump when that part is done.  So the
+ *               two warps of every scheduler belong to different groups, half a tile apart in time, and the arithmetic
+ *               of one hides the latencies of the other.
  * Every wait is bounded (clock64): a protocol error sets *error and ends the kernel, it cannot hang the GPU.
  *
- * Host emulation (tests/emu): only the epilogue threads run; the integer product is computed from the same B image and
- * the same source addressing, so the image layout, the quantisation and everything after TMEM are checked on the CPU.
+ * Host emulation (tests/emu): only the epilogue groups run (256 fibers); the integer product is computed from the same B
+ * image and the same source addressing, so the image layout, the quantisation and everything after TMEM are checked on
+ * the CPU.
  */
 #ifndef B200_WBFM_TC_CUH
 #define B200_WBFM_TC_CUH
@@ -56,40 +60,39 @@
 #define B200_TC_K_BYTES 512                          /* K of the product = bytes of one A row                   */
 #define B200_TC_KSTEPS 16                            /* MMAs of K = 32 per tile                                 */
 #define B200_TC_ROWS 125                             /* data rows per tile (TMEM lanes 125..127 idle)           */
-#define B200_TC_OPR 16                               /* stage-1 outputs per row                                 */
-#define B200_TC_OPT 8                                /* ... per epilogue thread (half a row)                    */
+#define B200_TC_OPR 16                               /* stage-1 outputs per row = per epilogue thread           */
 #define B200_TC_TILE_OUT (B200_TC_ROWS * B200_TC_OPR) /* 2000                                                   */
 #define B200_TC_TILE_BYTES (B200_TC_ROWS * B200_TC_ROW_BYTES) /* 40000                                          */
-#define B200_TC_N 112                                /* 3 slices x 2 half-rows x 9 outputs x (I, Q) = 108, padded */
-#define B200_TC_SLICE_COLS 36
-#define B200_TC_HALF_COLS 18
+#define B200_TC_SLICE_COLS 34                        /* 17 outputs x (I, Q)                                     */
+#define B200_TC_N 112                                /* 3 slices x 34 = 102, padded to a multiple of 16         */
 #define B200_TC_BOXES 8                              /* 64-byte K columns: 0..2 history, 3..7 the row           */
 #define B200_TC_A_BOX (128 * 64)                     /* 128 rows x 64 bytes of K, 64B swizzle                   */
 #define B200_TC_A_STAGE (B200_TC_BOXES * B200_TC_A_BOX)
 #define B200_TC_B_BOX (B200_TC_N * 64)
 #define B200_TC_B_BYTES (B200_TC_BOXES * B200_TC_B_BOX) /* 57344                                                */
 #define B200_TC_TX_BYTES (B200_TC_BOXES * B200_TC_ROWS * 64) /* bytes one tile's TMA copies deliver             */
-#define B200_TC_EPI 256
-#define B200_TC_THREADS (64 + B200_TC_EPI)
+#define B200_TC_GROUPS 2                             /* epilogue groups, taking the tiles in turn               */
+#define B200_TC_EPI 128                              /* threads per epilogue group                              */
+#define B200_TC_THREADS (64 + B200_TC_GROUPS * B200_TC_EPI)
 #define B200_TC_ACC_COLS 128                         /* TMEM columns per accumulator stage                      */
-#define B200_TC_APT 2                                 /* audio samples per thread in stage 2 (200 threads)       */
+#define B200_TC_APT 4                                /* audio samples per thread in stage 2 (100 threads)       */
 #define B200_TC_EBUF (B200_FM_HPAD + 128 * B200_TC_OPR + 16) /* floats per e[] buffer                           */
 
-#define B200_TC_SM_A 0
+#define B200_TC_SM_A 0                                                           /* [2] operand stages        */
 #define B200_TC_SM_B (B200_TC_SM_A + 2 * B200_TC_A_STAGE)
-#define B200_TC_SM_E (B200_TC_SM_B + B200_TC_B_BYTES)          /* float [2][52 + 2048 + 16]              */
-#define B200_TC_SM_TOT (B200_TC_SM_E + 2 * B200_TC_EBUF * 4)   /* float [2][256]                         */
-#define B200_TC_SM_CIN (B200_TC_SM_TOT + 2 * 256 * 4)          /* float [8 warps][256 + 8]               */
-#define B200_TC_SM_BAR (B200_TC_SM_CIN + 8 * 264 * 4)          /* u64 [8]                                */
-#define B200_TC_SM_MISC (B200_TC_SM_BAR + 64)                  /* u32 [4]                                */
+#define B200_TC_SM_E (B200_TC_SM_B + B200_TC_B_BYTES)                            /* float [group][2][EBUF]    */
+#define B200_TC_SM_TOT (B200_TC_SM_E + B200_TC_GROUPS * 2 * B200_TC_EBUF * 4)    /* float [3][128]            */
+#define B200_TC_SM_CNT (B200_TC_SM_TOT + 3 * 128 * 4)                            /* u32 [2] (+ pad)           */
+#define B200_TC_SM_BAR (B200_TC_SM_CNT + 16)                                     /* u64 [8]                   */
+#define B200_TC_SM_MISC (B200_TC_SM_BAR + 64)                                    /* u32 [4]                   */
 #define B200_TC_SMEM_BYTES (B200_TC_SM_MISC + 16)
 
 /* byte offset of element (row n, K byte k) inside an operand of `rows` rows: K-major, 64-byte swizzle
  * (cute Swizzle<2,4,3>): columns of 64 K-bytes, row pitch 64, the 16-byte chunk index XORed with (row / 2) % 4 */
 #define B200_TC_OP_OFF(rows, n, k) \
     ((uint32_t)(((k) >> 6) * ((rows) * 64) + (n) * 64 + (((((k) & 63) >> 4) ^ (((n) >> 1) & 3)) << 4) + ((k) & 15)))
-/* accumulator column of (slice s, half-row h, output j of the half-row's nine, component c) */
-#define B200_TC_COL(s, h, j, c) (B200_TC_SLICE_COLS * (s) + B200_TC_HALF_COLS * (h) + 2 * (j) + (c))
+/* accumulator column of (slice s, output j of the row's seventeen (o = j - 1), component c) */
+#define B200_TC_COL(s, j, c) (B200_TC_SLICE_COLS * (s) + 2 * (j) + (c))
 
 struct FmTcConsts {
     float b0;            /* 127.5 sum q0: the offset's share of the leading slice (exact in fp32)              */
@@ -97,10 +100,8 @@ struct FmTcConsts {
     float k12;           /* -127.5 (c1 sum q1 + c2 sum q2)                                                     */
     float b0_first[16];  /* the same for the first row of a capture, whose history bytes are zero-filled:      */
     float k12_first[16]; /* output o sees real samples through taps t <= 10 o only (x[n < 0] = 0)              */
-    float apow[8];       /* a^(i+1)                                                                            */
-    float a8p[9];        /* (a^8)^j, j = 0..8                                                                  */
-    float a64pow[5];     /* (a^64)^(2^s): one lane of the totals scan covers 8 half-rows = 64 outputs          */
-    float a8;
+    float apow[16];      /* a^(i+1)                                                                            */
+    float a16pow[5];     /* (a^16)^(2^s): decay over 2^s rows                                                  */
     float alpha;
     float h2[B200_FM_T2];
 };
@@ -207,11 +208,22 @@ B200_DEV void b200_tc_cp16(uint32_t sdst, const void *gsrc, uint32_t src_bytes)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
-B200_DEV void b200_tc_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+/* named barrier of one epilogue group (128 threads) */
+B200_DEV void b200_tc_epi_sync(int grp)
+{
+    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+B200_DEV void b200_tc_ld2(uint32_t taddr, uint32_t &a, uint32_t &b)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+B200_DEV long long b200_tc_clock() { return clock64(); }
 
 #else
 
-B200_DEV void b200_tc_epi_sync() { __syncthreads(); }
+B200_DEV void b200_tc_epi_sync(int grp) { emu::named_barrier(1 + grp, 128); }
+B200_DEV long long b200_tc_clock() { emu::yield_now(); return 0; } /* a poll of the other group: let its fibers run */
 
 #endif
 
@@ -246,36 +258,6 @@ B200_DEV bool b200_tc_src(int64_t R, int box, int chunk, uint64_t capture_bytes,
     return off + 16 <= (int64_t)capture_bytes;
 }
 
-/* ---- The 240 kS/s stages, run by the 256 epilogue threads in three phases that are software-pipelined over the tiles
- * of a work item with ONE CTA-wide barrier per tile:
- *     A(t)  accumulators -> y1 -> discriminator -> thread-serial de-emphasis of the thread's 8 outputs (registers),
- *           half-row total -> s_tot[t & 1]
- *     ---- barrier ----
- *     C(t-1) /5 FIR of the PREVIOUS tile out of s_e[(t-1) & 1] (complete since the barrier)
- *     B1(t) every warp scans the 250 half-row totals itself -> carried-in values in its scratch   } the TMEM loads of tile
- *     A(t+1)                                                                                     } t+1 are in flight
- *     B2(t) adds the carried-in part to the thread's e[] -> s_e[t & 1]                            } under B1
- * so the long dependent chain of the scan hides behind the accumulator loads and the arithmetic of the next tile, and
- * nothing waits on a second barrier.  acc[32 s + 2 j + c] = column B200_TC_COL(s, h, j, c) as loaded.  row = TMEM lane, h = half-row,
- * et = index among the epilogue threads, ws = epilogue warp index (scratch slot). ---- */
-struct FmTcTile {
-    uint32_t tile, it;
-    int last;      /* last row of the tile that holds samples */
-    bool store;
-    uint64_t m0;
-};
-B200_DEV FmTcTile b200_tc_tile(const FmTcParams &p, const FmTcItem &w, uint32_t tile, uint32_t it)
-{
-    FmTcTile t;
-    t.tile = tile;
-    t.it = it;
-    t.store = tile >= w.t_first_store;
-    t.m0 = (uint64_t)tile * B200_TC_TILE_OUT;
-    t.last = (int)(p.total_rows - tile * B200_TC_ROWS) - 1;
-    if (t.last > B200_TC_ROWS - 1) t.last = B200_TC_ROWS - 1;
-    return t;
-}
-
 /* atan2 as in wbfm.cuh with a degree-13 odd polynomial (7 coefficients, 3.2e-7 rad in fp32) */
 B200_DEV float b200_tc_atan2(float y, float x)
 {
@@ -296,137 +278,135 @@ B200_DEV float b200_tc_atan2(float y, float x)
     return copysignf(r, y);
 }
 
-/* FIRST: the tile holds the first row of a capture (tile 0), whose history bytes are zeros, not samples */
+/* ---- The 240 kS/s stages.  Tile n of the CTA's sequence belongs to epilogue group n & 1 (= its TMEM stage); a thread = a
+ * row = 16 outputs.  Per tile, in the group:
+ *     A(n)   accumulators -> y1 -> discriminator -> thread-serial de-emphasis of the row (registers), row total -> s_tot[n % 3]
+ *     ---- the group's barrier ----
+ *     C      /5 FIR of the group's PREVIOUS tile out of its e[] buffer (complete since the barrier)
+ *     wait until the other group has finished B(n - 1)
+ *     B(n)   shuffle scans of the row totals (this tile's and the last 32 rows of tile n - 1) -> carried-in value -> e[] of
+ *            the row -> the group's e[] buffer (n / 2) & 1, with the newest e[] of tile n - 1 in front of it; bump the counter
+ * row = TMEM lane, q = row / 32 = the warp's lane quarter, et = index among the group's epilogue threads. ---- */
+struct FmTcTile {
+    uint32_t tile, it;
+    int last;      /* last row of the tile that holds samples */
+    bool store;
+    uint64_t m0;
+};
+B200_DEV FmTcTile b200_tc_tile(const FmTcParams &p, const FmTcItem &w, uint32_t tile, uint32_t it)
+{
+    FmTcTile t;
+    t.tile = tile;
+    t.it = it;
+    t.store = tile >= w.t_first_store;
+    t.m0 = (uint64_t)tile * B200_TC_TILE_OUT;
+    t.last = (int)(p.total_rows - tile * B200_TC_ROWS) - 1;
+    if (t.last > B200_TC_ROWS - 1) t.last = B200_TC_ROWS - 1;
+    return t;
+}
+
+/* y1 of the row from the three accumulator slices: y = (d0 - 127.5 sum q0) c0 + (128 d1 + d2) c2 - 127.5 (c1 sum q1 + c2
+ * sum q2).  The leading slice loses its offset exactly (integer minus half-integer, both below 2^23), the two small
+ * slices are joined as integers.  lo[2 j + c] = 128 d1 + d2 as a float, d0[2 j + c] the leading slice.
+ * FIRST: the tile holds the first row of a capture (tile 0), whose history bytes are zeros, not samples. */
 template <bool FIRST>
-B200_DEV void b200_tc_phase_a(const FmTcParams &p, const FmTcItem &w, const FmTcTile &t, const uint32_t (&acc)[96], int row, int h,
-                              float (&e)[B200_TC_OPT], unsigned char *smem)
+B200_DEV void b200_tc_phase_a(const FmTcParams &p, const FmTcItem &w, const FmTcTile &t, const float (&lo)[B200_TC_SLICE_COLS],
+                              const uint32_t (&d0)[B200_TC_SLICE_COLS], int row, float (&e)[B200_TC_OPR], float *s_tot)
 {
     const FmTcConsts *k = &c_fm_tc;
-    float *s_tot = reinterpret_cast<float *>(smem + B200_TC_SM_TOT) + (t.it & 1u) * 256;
-    const int idx = 2 * row + h; /* position of this half-row in the tile */
-    /* slices -> y1 = (d0 - 127.5 sum q0) c0 + (128 d1 + d2) c2 - 127.5 (c1 sum q1 + c2 sum q2): the leading slice loses
-     * its offset exactly (integer minus half-integer, both below 2^23), the two small slices are joined as integers */
-    float yr[B200_TC_OPT + 1], yi[B200_TC_OPT + 1]; /* [0] = the output before this half-row */
     const bool first_row = FIRST && row == 0;
     const float c0 = k->c0, c2 = k->c2;
+    const float alpha = k->alpha, a1 = 1.0f - alpha;
+    float pr, pi, run = 0.0f; /* previous output; de-emphasis state from zero */
+    {
+        const float b0 = k->b0, k12 = k->k12; /* j = 0 is output -1: of row 0 of a capture it is y1[-1], never used */
+        pr = fmaf((float)(int32_t)d0[0] - b0, c0, fmaf(lo[0], c2, k12));
+        pi = fmaf((float)(int32_t)d0[1] - b0, c0, fmaf(lo[1], c2, k12));
+    }
+    float d[B200_TC_OPR];
 #pragma unroll
-    for (int j = 0; j <= B200_TC_OPT; ++j) {
-        const int o = 8 * h - 1 + j;
+    for (int i = 0; i < B200_TC_OPR; ++i) {
         float b0 = k->b0, k12 = k->k12;
-        if (FIRST && first_row && o >= 0) { b0 = k->b0_first[o < 0 ? 0 : o]; k12 = k->k12_first[o < 0 ? 0 : o]; }
-        const float r0 = (float)(int32_t)acc[2 * j] - b0, q0 = (float)(int32_t)acc[2 * j + 1] - b0;
-        const float r12 = (float)((int32_t)acc[32 + 2 * j] * 128 + (int32_t)acc[64 + 2 * j]);
-        const float q12 = (float)((int32_t)acc[32 + 2 * j + 1] * 128 + (int32_t)acc[64 + 2 * j + 1]);
-        yr[j] = fmaf(r0, c0, fmaf(r12, c2, k12));
-        yi[j] = fmaf(q0, c0, fmaf(q12, c2, k12));
-    }
-    float d[B200_TC_OPT];
-#pragma unroll
-    for (int i = 0; i < B200_TC_OPT; ++i) {
-        const float zr = fmaf(yr[i + 1], yr[i], yi[i + 1] * yi[i]);
-        const float zi = fmaf(yi[i + 1], yr[i], -(yr[i + 1] * yi[i]));
+        if (FIRST && first_row) { b0 = k->b0_first[i]; k12 = k->k12_first[i]; }
+        const float yr = fmaf((float)(int32_t)d0[2 * i + 2] - b0, c0, fmaf(lo[2 * i + 2], c2, k12));
+        const float yi = fmaf((float)(int32_t)d0[2 * i + 3] - b0, c0, fmaf(lo[2 * i + 3], c2, k12));
+        const float zr = fmaf(yr, pr, yi * pi);
+        const float zi = fmaf(yi, pr, -(yr * pi));
         d[i] = b200_tc_atan2(zi, zr);
+        pr = yr;
+        pi = yi;
     }
-    if (FIRST && idx == 0) d[0] = 0.0f; /* y1[-1] = 0: defined as d[0] = 0 */
+    if (FIRST && row == 0) d[0] = 0.0f; /* y1[-1] = 0: defined as d[0] = 0 */
     if (p.disc && t.store && row < B200_TC_ROWS) { /* lanes 125..127 hold no row of this tile */
-        const uint64_t m = t.m0 + (uint64_t)idx * B200_TC_OPT;
+        const uint64_t m = t.m0 + (uint64_t)row * B200_TC_OPR;
         float *dst = p.disc + (uint64_t)w.capture * p.disc_stride + m;
-        const int n_valid = p.m1 > m ? (p.m1 - m > B200_TC_OPT ? B200_TC_OPT : (int)(p.m1 - m)) : 0;
+        const int n_valid = p.m1 > m ? (p.m1 - m > B200_TC_OPR ? B200_TC_OPR : (int)(p.m1 - m)) : 0;
 #pragma unroll
-        for (int i = 0; i < B200_TC_OPT; ++i)
+        for (int i = 0; i < B200_TC_OPR; ++i)
             if (i < n_valid) dst[i] = d[i];
     }
-    const float alpha = k->alpha, a1 = 1.0f - alpha;
-    float run = 0.0f;
 #pragma unroll
-    for (int i = 0; i < B200_TC_OPT; ++i) {
+    for (int i = 0; i < B200_TC_OPR; ++i) {
         run = fmaf(a1, run, alpha * d[i]);
         e[i] = run;
     }
-    s_tot[idx] = run;
+    s_tot[row] = run;
 }
 
-/* after the tile's barrier: S[i] = a^8 S[i-1] + tot[i], S[-1] = cw (e[] just before the tile, carried in a register by
- * every thread); cin[i] = S[i-1] = e[] just before half-row i; lane l of every warp takes half-rows 8 l .. 8 l + 7 */
-B200_DEV void b200_tc_phase_b1(const FmTcTile &t, int et, int ws, float cw, unsigned char *smem)
+/* The de-emphasis state in front of every row.  S[r] = a^16 S[r-1] + tot[r]; what lies more than 512 outputs = 32 rows back
+ * has decayed by a^512 = 4e-13 (far below one fp32 ulp), so a warp scans the totals of its own 32 rows and of the 32 rows
+ * before them (for the first quarter: rows 93..124 of the previous tile, which is always a full one; zeros at the start of
+ * a work item) with two interleaved shuffle scans -- no shared-memory round trip, no carry from warp to warp.  Then e[] of
+ * the row gets its carried-in part and goes to the group's e[] buffer. */
+B200_DEV void b200_tc_phase_b(const FmTcTile &t, float (&e)[B200_TC_OPR], int row, int et, float lane_pow, float *s_e_cur,
+                              const float *s_e_prev, const float *s_tot, const float *s_tot_prev)
 {
     const FmTcConsts *k = &c_fm_tc;
-    float *s_e_cur = reinterpret_cast<float *>(smem + B200_TC_SM_E) + (t.it & 1u) * B200_TC_EBUF;
-    const float *s_e_prev = reinterpret_cast<const float *>(smem + B200_TC_SM_E) + ((t.it & 1u) ^ 1u) * B200_TC_EBUF;
-    const float *s_tot = reinterpret_cast<const float *>(smem + B200_TC_SM_TOT) + (t.it & 1u) * 256;
-    float *s_cin = reinterpret_cast<float *>(smem + B200_TC_SM_CIN) + ws * 264;
-    const int lane = et & 31;
+    const int lane = row & 31, q = row >> 5;
     /* the 49 (52) newest e[] of the previous tile go in front of this tile's buffer (zeros at the start of a work item;
-     * the previous tile of an item is always a full one and complete since the barrier) */
-    if (et < B200_FM_HPAD) s_e_cur[et] = t.it ? s_e_prev[B200_TC_TILE_OUT + et] : 0.0f;
-    const float4 ta = reinterpret_cast<const float4 *>(s_tot)[2 * lane], tb = reinterpret_cast<const float4 *>(s_tot)[2 * lane + 1];
-    const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-    float P[8], run = 0.0f;
+     * the previous tile of an item is always a full one) */
+    if (et < B200_FM_HPAD) s_e_cur[et] = t.it ? s_e_prev[B200_FM_HPAD + B200_TC_TILE_OUT - B200_FM_HPAD + et] : 0.0f;
+    float v = s_tot[row];
+    float u = q ? s_tot[row - 32] : (t.it ? s_tot_prev[B200_TC_ROWS - 32 + lane] : 0.0f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        run = fmaf(k->a8, run, tt[j]);
-        P[j] = run;
+    for (int s = 0; s < 5; ++s) {
+        const float nv = __shfl_up_sync(0xffffffffu, v, 1u << s), nu = __shfl_up_sync(0xffffffffu, u, 1u << s);
+        if (lane >= (1 << s)) {
+            v = fmaf(k->a16pow[s], nv, v);
+            u = fmaf(k->a16pow[s], nu, u);
+        }
     }
-    float v = run;
+    float excl = __shfl_up_sync(0xffffffffu, v, 1u); /* state built up inside the quarter in front of this row */
+    if (lane == 0) excl = 0.0f;
+    const float behind_prev = __shfl_sync(0xffffffffu, u, 31); /* state behind the 32 rows before the quarter */
+    const float cin = fmaf(lane_pow, behind_prev, excl);       /* lane_pow = (a^16)^lane */
 #pragma unroll
-    for (int s = 0; s < 3; ++s) { /* 8 lanes = 512 outputs back: what lies further has decayed by a^512 = 4e-13 */
-        const float u = __shfl_up_sync(0xffffffffu, v, 1u << s);
-        if (lane >= (1 << s)) v = fmaf(k->a64pow[s], u, v);
-    }
-    float vprev = __shfl_up_sync(0xffffffffu, v, 1u);
-    if (lane == 0) vprev = 0.0f;
-    float lane_pow = 1.0f; /* (a^64)^lane */
+    for (int i = 0; i < B200_TC_OPR; ++i) e[i] = fmaf(k->apow[i], cin, e[i]);
+    float4 *de = reinterpret_cast<float4 *>(s_e_cur + B200_FM_HPAD + row * B200_TC_OPR);
 #pragma unroll
-    for (int s = 0; s < 5; ++s)
-        if (lane & (1 << s)) lane_pow *= k->a64pow[s];
-    const float lin = fmaf(lane_pow, cw, vprev); /* S[8 lane - 1] */
-    float c[8];
-    c[0] = lin;
-#pragma unroll
-    for (int j = 1; j < 8; ++j) c[j] = fmaf(k->a8p[j], lin, P[j - 1]);
-    float4 *dst = reinterpret_cast<float4 *>(s_cin + 8 * lane);
-    dst[0] = make_float4(c[0], c[1], c[2], c[3]);
-    dst[1] = make_float4(c[4], c[5], c[6], c[7]);
-}
-/* ... second part: add the carried-in part to the thread's e[] -> s_e[t & 1] */
-B200_DEV void b200_tc_phase_b2(const FmTcTile &t, float (&e)[B200_TC_OPT], int row, int h, int ws, float &cw, unsigned char *smem)
-{
-    const FmTcConsts *k = &c_fm_tc;
-    float *s_e_cur = reinterpret_cast<float *>(smem + B200_TC_SM_E) + (t.it & 1u) * B200_TC_EBUF;
-    const float *s_cin = reinterpret_cast<const float *>(smem + B200_TC_SM_CIN) + ws * 264;
-    const int idx = 2 * row + h;
-    __syncwarp();
-    const float cin = s_cin[idx];
-    cw = s_cin[2 * t.last + 2]; /* S[2 last + 1] = e[] after the last row that holds samples (2 last + 2 <= 250) */
-    __syncwarp();               /* the scratch is rewritten by this warp in the next tile */
-#pragma unroll
-    for (int i = 0; i < B200_TC_OPT; ++i) e[i] = fmaf(k->apow[i], cin, e[i]);
-    float4 *de = reinterpret_cast<float4 *>(s_e_cur + B200_FM_HPAD + idx * B200_TC_OPT);
-    de[0] = make_float4(e[0], e[1], e[2], e[3]);
-    de[1] = make_float4(e[4], e[5], e[6], e[7]);
+    for (int i = 0; i < B200_TC_OPR / 4; ++i) de[i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
 }
 
-/* stage 2 of a tile whose e[] is complete: audio[p] = sum_k h2[k] e[5 p - k].  A tile starts at a multiple of 10 stage-1
- * outputs; thread et < 200 owns the two audio samples p = m0 / 5 + 2 et + r whose window e[10 et - 49 .. 10 et + 5] is read
- * with 28 aligned 64-bit loads from one float in front of it. */
-B200_DEV void b200_tc_phase_c(const FmTcParams &p, const FmTcItem &w, const FmTcTile &t, int et, unsigned char *smem)
+/* stage 2 of a tile whose e[] is complete: audio[p] = sum_k h2[k] e[5 p - k].  A tile starts at a multiple of 20 stage-1
+ * outputs; thread et < 100 owns the four audio samples p = m0 / 5 + 4 et + r whose window e[20 et - 49 .. 20 et + 15] sits
+ * at the fixed offset 3 behind the 16-byte aligned address s_e + 20 et: 17 128-bit loads, taps outermost (wbfm.cuh) */
+B200_DEV void b200_tc_phase_c(const FmTcParams &p, uint32_t capture, const FmTcTile &t, int et, const float *s_e)
 {
     const FmTcConsts *k = &c_fm_tc;
-    const float *s_e = reinterpret_cast<const float *>(smem + B200_TC_SM_E) + (t.it & 1u) * B200_TC_EBUF;
     uint64_t mg_end = t.m0 + (uint64_t)(t.last + 1) * B200_TC_OPR;
     if (mg_end > p.m1) mg_end = p.m1;
     const uint64_t pg_first = t.m0 / B200_FM_D2;
     const uint64_t pg_end = (mg_end + B200_FM_D2 - 1) / B200_FM_D2;
     const uint64_t pg0 = pg_first + (uint64_t)et * B200_TC_APT;
     if (et < B200_TC_TILE_OUT / (B200_FM_D2 * B200_TC_APT) && pg0 < pg_end) {
-        constexpr int WOFF = 1;                                                              /* ew[j] = e[10 et - 50 + j] */
-        constexpr int NW2 = (WOFF + B200_FM_T2 + B200_FM_D2 * (B200_TC_APT - 1) + 1) / 2;    /* 28 */
-        const float2 *win = reinterpret_cast<const float2 *>(s_e + B200_FM_HPAD - B200_FM_HIST - WOFF + et * (B200_FM_D2 * B200_TC_APT));
-        float ew[2 * NW2];
+        constexpr int WOFF = B200_FM_HPAD - B200_FM_HIST; /* 3 */
+        constexpr int NW4 = (WOFF + B200_FM_T2 + B200_FM_D2 * (B200_TC_APT - 1) + 3) / 4; /* 17 */
+        const float4 *win = reinterpret_cast<const float4 *>(s_e + et * (B200_FM_D2 * B200_TC_APT));
+        float ew[4 * NW4];
 #pragma unroll
-        for (int j = 0; j < NW2; ++j) {
-            const float2 q = win[j];
-            ew[2 * j] = q.x; ew[2 * j + 1] = q.y;
+        for (int j = 0; j < NW4; ++j) {
+            const float4 v = win[j];
+            ew[4 * j] = v.x; ew[4 * j + 1] = v.y; ew[4 * j + 2] = v.z; ew[4 * j + 3] = v.w;
         }
         float au[B200_TC_APT];
 #pragma unroll
@@ -438,7 +418,7 @@ B200_DEV void b200_tc_phase_c(const FmTcParams &p, const FmTcItem &w, const FmTc
             for (int r = 0; r < B200_TC_APT; ++r) au[r] = fmaf(hk, ew[WOFF + B200_FM_HIST + B200_FM_D2 * r - tp], au[r]);
         }
         if (t.store) {
-            float *dst = p.audio + (uint64_t)w.capture * p.audio_stride + pg0;
+            float *dst = p.audio + (uint64_t)capture * p.audio_stride + pg0;
 #pragma unroll
             for (int r = 0; r < B200_TC_APT; ++r)
                 if (pg0 + r < pg_end) dst[r] = au[r];
@@ -446,9 +426,68 @@ B200_DEV void b200_tc_phase_c(const FmTcParams &p, const FmTcItem &w, const FmTc
     }
 }
 
+/* the epilogue group's walk over the CTA's tiles; `take(w, tile, it, n, e)` fetches the accumulators of the tile with
+ * running index n and runs phase A into e[] (device: TMEM loads; emulation: the integer product on the host) */
+template <class Take>
+B200_DEV bool b200_tc_epilogue_group(const FmTcParams &p, uint32_t n_items, uint32_t first_item, uint32_t item_step, int grp, int row, int et,
+                                     unsigned char *smem, volatile uint32_t *abort_flag, Take take)
+{
+    float *s_e_grp = reinterpret_cast<float *>(smem + B200_TC_SM_E);
+    float *s_tot = reinterpret_cast<float *>(smem + B200_TC_SM_TOT);
+    volatile uint32_t *s_cnt = reinterpret_cast<volatile uint32_t *>(smem + B200_TC_SM_CNT);
+    const int lane = row & 31;
+    float lane_pow = 1.0f; /* (a^16)^lane */
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+        if (lane & (1 << s)) lane_pow *= c_fm_tc.a16pow[s];
+    bool have_pend = false;
+    uint32_t pend_capture = 0, pend_n = 0;
+    FmTcTile pend_t{};
+    uint32_t n = 0; /* running tile index of the CTA */
+    for (uint32_t item = first_item; item < n_items; item += item_step) {
+        const FmTcItem w = b200_tc_item(p, item);
+        for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it, ++n) {
+            if ((int)(n & 1u) != grp) continue;
+            const FmTcTile t = b200_tc_tile(p, w, tile, it);
+            float e[B200_TC_OPR];
+            if (!take(w, t, n, e, s_tot + (n % 3u) * 128)) return false;
+            if (p.dbg_flags & 2u) continue;
+            b200_tc_epi_sync(grp); /* the group's row totals of tile n and its e[] of its previous tile are complete */
+            if (have_pend) b200_tc_phase_c(p, pend_capture, pend_t, et, s_e_grp + (grp * 2 + ((pend_n >> 1) & 1u)) * B200_TC_EBUF);
+            /* tile n - 1 is the other group's: its phase B (hence its row totals and its e[]) must be done.  Always waited
+             * for, also at the start of a work item, so the groups never drift more than one tile apart (buffer reuse) */
+            if (n > 0) {
+                const uint32_t need = 4u * ((n - 1u) / 2u + 1u);
+                const long long t0 = b200_tc_clock();
+                while (s_cnt[grp ^ 1] < need) {
+                    if (*abort_flag || b200_tc_clock() - t0 > (1ll << 28)) return false;
+                }
+                __threadfence_block();
+            }
+            b200_tc_phase_b(t, e, row, et, lane_pow, s_e_grp + (grp * 2 + ((n >> 1) & 1u)) * B200_TC_EBUF,
+                            s_e_grp + ((grp ^ 1) * 2 + (((n - 1u) >> 1) & 1u)) * B200_TC_EBUF, s_tot + (n % 3u) * 128,
+                            s_tot + ((n + 2u) % 3u) * 128);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(const_cast<uint32_t *>(s_cnt) + grp, 1u);
+            }
+            have_pend = true;
+            pend_capture = w.capture;
+            pend_t = t;
+            pend_n = n;
+        }
+    }
+    if (have_pend && !(p.dbg_flags & 2u)) { /* drain: the audio of the group's last tile */
+        b200_tc_epi_sync(grp);
+        b200_tc_phase_c(p, pend_capture, pend_t, et, s_e_grp + (grp * 2 + ((pend_n >> 1) & 1u)) * B200_TC_EBUF);
+    }
+    return true;
+}
+
 #ifdef B200_EMULATED
 /* the integer product as the tensor cores compute it, from the same source addressing and the same B image */
-static void b200_tc_emulated_acc(const FmTcParams &p, const FmTcItem &w, uint32_t tile, int row, int h, uint32_t (&acc)[96])
+static void b200_tc_emulated_acc(const FmTcParams &p, const FmTcItem &w, uint32_t tile, int row, int32_t (&acc)[3 * B200_TC_SLICE_COLS])
 {
     const uint8_t *cap = p.iq + (uint64_t)w.capture * p.capture_stride;
     uint8_t a[B200_TC_K_BYTES];
@@ -457,15 +496,11 @@ static void b200_tc_emulated_acc(const FmTcParams &p, const FmTcItem &w, uint32_
         const bool valid = b200_tc_src((int64_t)tile * B200_TC_ROWS + row, kk >> 6, (kk & 63) >> 4, p.capture_bytes, off);
         a[kk] = valid ? cap[off + (kk & 15)] : 0;
     }
-    for (int n = 0; n < 96; ++n) acc[n] = 0xdeadu;
-    for (int s = 0; s < 3; ++s)
-        for (int jc = 0; jc < 32; ++jc) { /* the x32 load: 32 consecutive columns from B200_TC_COL(s, h, 0, 0) */
-            const int n = B200_TC_SLICE_COLS * s + B200_TC_HALF_COLS * h + jc;
-            if (n >= B200_TC_N) continue;
-            int64_t sum = 0;
-            for (int kk = 0; kk < B200_TC_K_BYTES; ++kk) sum += (int64_t)a[kk] * (int64_t)(int8_t)p.b_image[B200_TC_OP_OFF(B200_TC_N, n, kk)];
-            acc[32 * s + jc] = (uint32_t)(int32_t)sum;
-        }
+    for (int n = 0; n < 3 * B200_TC_SLICE_COLS; ++n) {
+        int64_t sum = 0;
+        for (int kk = 0; kk < B200_TC_K_BYTES; ++kk) sum += (int64_t)a[kk] * (int64_t)(int8_t)p.b_image[B200_TC_OP_OFF(B200_TC_N, n, kk)];
+        acc[n] = (int32_t)sum;
+    }
 }
 #endif
 
@@ -479,39 +514,28 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
     const int tid = (int)threadIdx.x;
     const uint32_t n_items = p.segments * p.n_captures;
 #ifdef B200_EMULATED
-    /* 256 threads: the epilogue role only */
-    const int row = tid & 127, h = tid >> 7;
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const FmTcItem w = b200_tc_item(p, item);
-        float cw = 0.0f;
-        float e_cur[B200_TC_OPT], e_next[B200_TC_OPT];
-        auto phase_a = [&](uint32_t tile, uint32_t it, float (&e)[B200_TC_OPT]) {
-            const FmTcTile t = b200_tc_tile(p, w, tile, it);
-            uint32_t acc[96];
-            if (row < B200_TC_ROWS) b200_tc_emulated_acc(p, w, tile, row, h, acc);
-            else for (int n = 0; n < 96; ++n) acc[n] = 0x12345u * (uint32_t)(n + tid); /* idle lanes hold anything */
-            if (p.dbg_acc && w.capture == 0 && tile == 0)
-                for (int s = 0; s < 3; ++s)
-                    for (int jc = 0; jc < B200_TC_HALF_COLS; ++jc)
-                        p.dbg_acc[row * B200_TC_N + B200_TC_SLICE_COLS * s + B200_TC_HALF_COLS * h + jc] = (int32_t)acc[32 * s + jc];
-            if (tile == 0) b200_tc_phase_a<true>(p, w, t, acc, row, h, e, smem);
-            else b200_tc_phase_a<false>(p, w, t, acc, row, h, e, smem);
-        };
-        if (w.t_end > w.t_begin) phase_a(w.t_begin, 0, e_cur);
-        for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it) {
-            const FmTcTile t = b200_tc_tile(p, w, tile, it);
-            b200_tc_epi_sync();
-            if (it) b200_tc_phase_c(p, w, b200_tc_tile(p, w, tile - 1, it - 1), tid, smem);
-            b200_tc_phase_b1(t, tid, tid >> 5, cw, smem);
-            if (tile + 1 < w.t_end) phase_a(tile + 1, it + 1, e_next);
-            b200_tc_phase_b2(t, e_cur, row, h, tid >> 5, cw, smem);
-            for (int i = 0; i < B200_TC_OPT; ++i) e_cur[i] = e_next[i];
+    /* 256 fibers: the two epilogue groups only */
+    const int grp = tid >> 7, row = tid & 127;
+    uint32_t abort_never = 0;
+    if (tid < 2) reinterpret_cast<uint32_t *>(smem + B200_TC_SM_CNT)[tid] = 0u;
+    __syncthreads();
+    auto take = [&](const FmTcItem &w, const FmTcTile &t, uint32_t, float (&e)[B200_TC_OPR], float *s_tot) -> bool {
+        int32_t acc[3 * B200_TC_SLICE_COLS];
+        if (row < B200_TC_ROWS) b200_tc_emulated_acc(p, w, t.tile, row, acc);
+        else for (int n = 0; n < 3 * B200_TC_SLICE_COLS; ++n) acc[n] = 0x12345 * (n + tid); /* idle lanes hold anything */
+        if (p.dbg_acc && w.capture == 0 && t.tile == 0)
+            for (int n = 0; n < 3 * B200_TC_SLICE_COLS; ++n) p.dbg_acc[row * B200_TC_N + n] = acc[n];
+        float lo[B200_TC_SLICE_COLS];
+        uint32_t d0[B200_TC_SLICE_COLS];
+        for (int n = 0; n < B200_TC_SLICE_COLS; ++n) {
+            lo[n] = (float)(acc[B200_TC_SLICE_COLS + n] * 128 + acc[2 * B200_TC_SLICE_COLS + n]);
+            d0[n] = (uint32_t)acc[n];
         }
-        if (w.t_end > w.t_begin) {
-            b200_tc_epi_sync();
-            b200_tc_phase_c(p, w, b200_tc_tile(p, w, w.t_end - 1, w.t_end - 1 - w.t_begin), tid, smem);
-        }
-    }
+        if (t.tile == 0) b200_tc_phase_a<true>(p, w, t, lo, d0, row, e, s_tot);
+        else b200_tc_phase_a<false>(p, w, t, lo, d0, row, e, s_tot);
+        return true;
+    };
+    b200_tc_epilogue_group(p, n_items, blockIdx.x, gridDim.x, grp, row, row, smem, &abort_never, take);
 #else
     const int warp = tid >> 5, lane = tid & 31;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + B200_TC_SM_BAR);
@@ -524,10 +548,12 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
             b200_tc_bar_init(bar_full + i, 1);
             b200_tc_bar_init(bar_empty + i, 1);
             b200_tc_bar_init(bar_tfull + i, 1);
-            b200_tc_bar_init(bar_tempty + i, B200_TC_EPI / 32); /* one arrival per epilogue warp */
+            b200_tc_bar_init(bar_tempty + i, B200_TC_EPI / 32); /* one arrival per warp of the stage's epilogue group */
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_misc[1] = 0u;
+        reinterpret_cast<uint32_t *>(smem + B200_TC_SM_CNT)[0] = 0u;
+        reinterpret_cast<uint32_t *>(smem + B200_TC_SM_CNT)[1] = 0u;
         if (p.manual_from_tile) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     if (warp == 1) { /* TMEM: two accumulator stages of 128 columns */
@@ -624,75 +650,58 @@ __global__ void __launch_bounds__(B200_TC_THREADS, 1) k_wbfm_tc(FmTcParams p)
         }
         __syncwarp();
     } else {
-        /* ===== epilogue ===== */
+        /* ===== epilogue group grp: the tiles with running index n = grp (mod 2), accumulator stage grp ===== */
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;              /* TMEM lane quarter this warp may read */
-        const int h = (warp - 2) >> 2;       /* half-row */
         const int row = q * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;
-        uint32_t g = 0;
-        bool ok = true;
-        /* accumulator columns of this thread: issue the three TMEM loads of the tile with running index g */
-        uint32_t v0[32], v1[32], v2[32];
-        auto acc_issue = [&](uint32_t gi) -> bool {
-            const uint32_t stage = gi & 1u, phase = (gi >> 1) & 1u;
-            if (!b200_tc_wait(bar_tfull + stage, phase, s_abort)) return false;
+        const int et = (warp - 2 - 4 * grp) * 32 + lane;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + grp * B200_TC_ACC_COLS;
+        auto take = [&](const FmTcItem &w, const FmTcTile &t, uint32_t n, float (&e)[B200_TC_OPR], float *s_tot) -> bool {
+            if (!b200_tc_wait(bar_tfull + grp, (n >> 1) & 1u, s_abort)) return false;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + stage * B200_TC_ACC_COLS + B200_TC_HALF_COLS * h;
-            b200_tc_ld32(taddr, v0);
-            b200_tc_ld32(taddr + B200_TC_SLICE_COLS, v1);
-            b200_tc_ld32(taddr + 2 * B200_TC_SLICE_COLS, v2);
-            return true;
-        };
-        /* ... wait for them, release the accumulator stage, run phase A */
-        auto acc_use = [&](const FmTcItem &w, uint32_t gi, uint32_t tile, uint32_t it, float (&e)[B200_TC_OPT]) {
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            uint32_t acc[96];
+            /* the two small slices first, joined as integers; then the leading one */
+            float lo[B200_TC_SLICE_COLS];
+            {
+                uint32_t v1[32], v2[32], w1a, w1b, w2a, w2b;
+                b200_tc_ld32(taddr + B200_TC_SLICE_COLS, v1);
+                b200_tc_ld2(taddr + B200_TC_SLICE_COLS + 32, w1a, w1b);
+                b200_tc_ld32(taddr + 2 * B200_TC_SLICE_COLS, v2);
+                b200_tc_ld2(taddr + 2 * B200_TC_SLICE_COLS + 32, w2a, w2b);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.dbg_acc && w.capture == 0 && t.tile == 0) {
 #pragma unroll
-            for (int n = 0; n < 32; ++n) { acc[n] = v0[n]; acc[32 + n] = v1[n]; acc[64 + n] = v2[n]; }
+                    for (int c = 0; c < B200_TC_SLICE_COLS; ++c) {
+                        p.dbg_acc[row * B200_TC_N + B200_TC_SLICE_COLS + c] = c < 32 ? (int32_t)v1[c < 32 ? c : 0] : (c == 32 ? (int32_t)w1a : (int32_t)w1b);
+                        p.dbg_acc[row * B200_TC_N + 2 * B200_TC_SLICE_COLS + c] = c < 32 ? (int32_t)v2[c < 32 ? c : 0] : (c == 32 ? (int32_t)w2a : (int32_t)w2b);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) lo[c] = (float)((int32_t)v1[c] * 128 + (int32_t)v2[c]);
+                lo[32] = (float)((int32_t)w1a * 128 + (int32_t)w2a);
+                lo[33] = (float)((int32_t)w1b * 128 + (int32_t)w2b);
+            }
+            uint32_t d0[B200_TC_SLICE_COLS];
+            {
+                uint32_t v0[32];
+                b200_tc_ld32(taddr, v0);
+                b200_tc_ld2(taddr + 32, d0[32], d0[33]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 32; ++c) d0[c] = v0[c];
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) b200_tc_arrive(bar_tempty + (gi & 1u)); /* the MMA warp may overwrite this accumulator */
-            if (p.dbg_acc && w.capture == 0 && tile == 0) {
+            if (lane == 0) b200_tc_arrive(bar_tempty + grp); /* the MMA lane may overwrite this accumulator */
+            if (p.dbg_acc && w.capture == 0 && t.tile == 0) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s)
-#pragma unroll
-                    for (int jc = 0; jc < B200_TC_HALF_COLS; ++jc)
-                        p.dbg_acc[row * B200_TC_N + B200_TC_SLICE_COLS * s + B200_TC_HALF_COLS * h + jc] = (int32_t)acc[32 * s + jc];
+                for (int c = 0; c < B200_TC_SLICE_COLS; ++c) p.dbg_acc[row * B200_TC_N + c] = (int32_t)d0[c];
             }
-            if (p.dbg_flags & 2u) return;
-            const FmTcTile t = b200_tc_tile(p, w, tile, it);
-            if (tile == 0) b200_tc_phase_a<true>(p, w, t, acc, row, h, e, smem);
-            else b200_tc_phase_a<false>(p, w, t, acc, row, h, e, smem);
+            if (p.dbg_flags & 2u) return true;
+            if (t.tile == 0) b200_tc_phase_a<true>(p, w, t, lo, d0, row, e, s_tot);
+            else b200_tc_phase_a<false>(p, w, t, lo, d0, row, e, s_tot);
+            return true;
         };
-        for (uint32_t item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
-            const FmTcItem w = b200_tc_item(p, item);
-            if (w.t_end <= w.t_begin) continue;
-            float cw = 0.0f;
-            float e_cur[B200_TC_OPT], e_next[B200_TC_OPT];
-            if (!acc_issue(g)) { ok = false; break; }
-            acc_use(w, g, w.t_begin, 0, e_cur);
-            ++g;
-            for (uint32_t tile = w.t_begin, it = 0; tile < w.t_end; ++tile, ++it) {
-                const bool more = tile + 1 < w.t_end;
-                if (p.dbg_flags & 2u) { /* timing experiment: accumulator traffic only */
-                    if (more) { if (!acc_issue(g)) { ok = false; break; } acc_use(w, g, tile + 1, it + 1, e_next); ++g; }
-                    continue;
-                }
-                const FmTcTile t = b200_tc_tile(p, w, tile, it);
-                b200_tc_epi_sync();
-                if (it) b200_tc_phase_c(p, w, b200_tc_tile(p, w, tile - 1, it - 1), et, smem);
-                if (more && !acc_issue(g)) { ok = false; break; } /* the next tile's accumulators are on their way ... */
-                b200_tc_phase_b1(t, et, warp - 2, cw, smem);        /* ... under the scan of this tile's totals        */
-                if (more) { acc_use(w, g, tile + 1, it + 1, e_next); ++g; }
-                b200_tc_phase_b2(t, e_cur, row, h, warp - 2, cw, smem);
-#pragma unroll
-                for (int i = 0; i < B200_TC_OPT; ++i) e_cur[i] = e_next[i];
-            }
-            if (ok && !(p.dbg_flags & 2u)) { /* drain: the audio of the item's last tile */
-                b200_tc_epi_sync();
-                b200_tc_phase_c(p, w, b200_tc_tile(p, w, w.t_end - 1, w.t_end - 1 - w.t_begin), et, smem);
-            }
-        }
+        const bool ok = b200_tc_epilogue_group(p, n_items, blockIdx.x, gridDim.x, grp, row, et, smem, s_abort, take);
         if (!ok && lane == 0) { *s_abort = 1u; atomicCAS(p.error, 0u, 4u); }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

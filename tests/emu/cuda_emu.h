@@ -69,6 +69,7 @@ struct State {
     uint32_t shfl_buf[1024];
     int bar_count, bar_gen;           /* block barrier */
     int wbar_count[32], wbar_gen[32]; /* per-warp barriers */
+    int nbar_count[16], nbar_gen[16]; /* named barriers (bar.sync id, count) */
 };
 inline State &S() { static State s; return s; }
 inline void trampoline()
@@ -102,6 +103,14 @@ inline void warp_barrier()
     if (++s.wbar_count[w] == members) { s.wbar_count[w] = 0; s.wbar_gen[w]++; }
     else while (s.wbar_gen[w] == g) yield_now();
 }
+/* bar.sync id, count: `count` fibers meet at barrier `id` */
+inline void named_barrier(int id, int count)
+{
+    State &s = S();
+    int g = s.nbar_gen[id];
+    if (++s.nbar_count[id] == count) { s.nbar_count[id] = 0; s.nbar_gen[id]++; }
+    else while (s.nbar_gen[id] == g) yield_now();
+}
 /* run one block */
 inline void run_block(const std::function<void()> &body)
 {
@@ -111,6 +120,7 @@ inline void run_block(const std::function<void()> &body)
     s.fibers.resize(n);
     s.bar_count = 0; s.bar_gen = 0;
     for (int w = 0; w < 32; ++w) { s.wbar_count[w] = 0; s.wbar_gen[w] = 0; }
+    for (int b = 0; b < 16; ++b) { s.nbar_count[b] = 0; s.nbar_gen[b] = 0; }
     const size_t STK = 256 * 1024;
     for (unsigned i = 0; i < n; ++i) {
         Fiber &f = s.fibers[i];

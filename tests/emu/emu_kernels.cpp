@@ -157,7 +157,7 @@ int emu_wbfm_tc_batch(const uint8_t *iq, uint32_t n_captures, uint64_t len_each_
     p.dbg_flags = 0;
     /* fewer CTAs than work items: every CTA walks several */
     const uint32_t items = pl.segments * n_captures;
-    emu::launch(dim3(items > 2 ? 2 : items, 1), dim3(B200_TC_EPI), B200_TC_SMEM_BYTES, [&] { k_wbfm_tc(p); });
+    emu::launch(dim3(items > 2 ? 2 : items, 1), dim3(B200_TC_GROUPS * B200_TC_EPI), B200_TC_SMEM_BYTES, [&] { k_wbfm_tc(p); });
     return e;
 }
 

@@ -220,16 +220,16 @@ def test_wbfm_tensor_engine_logic(emu, g, n, ncap, tps):
     assert np.max(np.abs(hq - h)) <= 2.0**-22 / 2.0**e * 1.001 and np.max(np.abs(hq - h)) < 4e-7 * np.max(np.abs(h))
     # raw accumulators of tile 0 = the integer FIR of the raw bytes, slice by slice (row 0: zero-filled history)
     u = iq[:nb].astype(np.int64)
-    # (column of (slice s, half-row hr, j, c) = 36 s + 18 hr + 2 j + c holds output o = 8 hr - 1 + j of the row)
+    # (column 34 s + 2 j + c holds output o = j - 1 of the row)
     for r in (0, 1, 7, 124):
-        for hr, j in ((0, 0), (0, 1), (0, 8), (1, 0), (1, 4), (1, 8)):
-            m = 16 * r + 8 * hr - 1 + j
+        for j in (0, 1, 8, 9, 16):
+            m = 16 * r - 1 + j
             if 10 * m >= n or m < 0:
                 continue
             for c in (0, 1):
                 for s in range(3):
                     want = sum(int(q[s][t]) * int(u[2 * (10 * m - t) + c]) for t in range(80) if 0 <= 10 * m - t < n)
-                    assert acc[r, 36 * s + 18 * hr + 2 * j + c] == want, (r, hr, j, c, s)
+                    assert acc[r, 34 * s + 2 * j + c] == want, (r, j, c, s)
     for c in range(ncap):
         ga, gd = g.wbfm(iq[c * nb:(c + 1) * nb], want_disc=True)
         derr = np.abs(wrap_phase(disc[c * m1:(c + 1) * m1] - gd))

@@ -242,10 +242,9 @@ def test_tensor_engine_accumulators_bit_exact(sdr_tc, g):
         for c in (0, 1):
             x = np.concatenate([np.zeros(96, np.int64), u[c::2]])           # x[n < 0] = 0
             full = np.convolve(x, q[s_].astype(np.int64))                    # full[96 + n] = sum_t q[t] x[n - t]
-            for hr in (0, 1):
-                for j in range(9):                                           # output m = 16 r + 8 hr - 1 + j, sample 10 m
-                    m = 16 * np.arange(125) + 8 * hr - 1 + j
-                    assert np.array_equal(acc[:125, 36 * s_ + 18 * hr + 2 * j + c], full[96 + 10 * m]), (s_, c, hr, j)
+            for j in range(17):                                              # output m = 16 r - 1 + j, sample 10 m
+                m = 16 * np.arange(125) - 1 + j
+                assert np.array_equal(acc[:125, 34 * s_ + 2 * j + c], full[96 + 10 * m]), (s_, c, j)
 
 
 @pytest.mark.parametrize("n_captures,len_each", [(1, 16), (1, 2416), (2, 262144), (3, 30720 * 5 + 240 * 3 + 16), (1, 4800000),
