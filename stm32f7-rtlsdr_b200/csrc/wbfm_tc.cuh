@@ -36,7 +36,8 @@
  *               then shuffle scans over the warp's 32 rows and the 32 rows before them -- what lies further back has
  *               decayed by a^512 = 4e-13 --, no shared-memory round trip), /5 FIR out of a shared window.  A group meets
  *               at its own 128-thread barrier once per tile; what a tile needs from the tile before it (the other group's:
- *               row totals, the newest 49 e[]) is ordered by a counter the groups bump when that part is done.  So the
+ *               row totals, the newest 49 e[]) is ordered by a producer / consumer named barrier (bar.arrive / bar.sync)
+ *               behind a bounded poll of a counter.  So the
  *               two warps of every scheduler belong to different groups, half a tile apart in time, and the arithmetic
  *               of one hides the latencies of the other.
  * Every wait is bounded (clock64): a protocol error sets *error and ends the kernel, it cannot hang the GPU.
@@ -219,11 +220,25 @@ B200_DEV void b200_tc_ld2(uint32_t taddr, uint32_t &a, uint32_t &b)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
 B200_DEV long long b200_tc_clock() { return clock64(); }
+/* "phase B of my tile is done" from one epilogue group to the other: the 128 threads of group grp arrive on named barrier
+ * 3 + grp, the 128 threads of the other group sync on it (256 participants) */
+B200_DEV void b200_tc_group_done(int grp)
+{
+    if (grp == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+    else asm volatile("bar.arrive 4, 256;" ::: "memory");
+}
+B200_DEV void b200_tc_group_wait(int other)
+{
+    if (other == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+    else asm volatile("bar.sync 4, 256;" ::: "memory");
+}
 
 #else
 
 B200_DEV void b200_tc_epi_sync(int grp) { emu::named_barrier(1 + grp, 128); }
 B200_DEV long long b200_tc_clock() { emu::yield_now(); return 0; } /* a poll of the other group: let its fibers run */
+B200_DEV void b200_tc_group_done(int grp) { emu::named_arrive(3 + grp, 256); }
+B200_DEV void b200_tc_group_wait(int other) { emu::named_barrier(3 + other, 256); }
 
 #endif
 
@@ -457,21 +472,22 @@ B200_DEV bool b200_tc_epilogue_group(const FmTcParams &p, uint32_t n_items, uint
             /* tile n - 1 is the other group's: its phase B (hence its row totals and its e[]) must be done.  Always waited
              * for, also at the start of a work item, so the groups never drift more than one tile apart (buffer reuse) */
             if (n > 0) {
+                /* bounded poll of the other group's counter first (a protocol error must end the kernel, not hang it), then
+                 * the named barrier its threads have arrived on: that is the synchronisation proper */
                 const uint32_t need = 4u * ((n - 1u) / 2u + 1u);
                 const long long t0 = b200_tc_clock();
                 while (s_cnt[grp ^ 1] < need) {
                     if (*abort_flag || b200_tc_clock() - t0 > (1ll << 28)) return false;
                 }
-                __threadfence_block();
+                b200_tc_group_wait(grp ^ 1);
             }
             b200_tc_phase_b(t, e, row, et, lane_pow, s_e_grp + (grp * 2 + ((n >> 1) & 1u)) * B200_TC_EBUF,
                             s_e_grp + ((grp ^ 1) * 2 + (((n - 1u) >> 1) & 1u)) * B200_TC_EBUF, s_tot + (n % 3u) * 128,
                             s_tot + ((n + 2u) % 3u) * 128);
+            __threadfence_block();
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                atomicAdd(const_cast<uint32_t *>(s_cnt) + grp, 1u);
-            }
+            if (lane == 0) atomicAdd(const_cast<uint32_t *>(s_cnt) + grp, 1u);
+            b200_tc_group_done(grp);
             have_pend = true;
             pend_capture = w.capture;
             pend_t = t;

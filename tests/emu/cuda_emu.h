@@ -111,6 +111,12 @@ inline void named_barrier(int id, int count)
     if (++s.nbar_count[id] == count) { s.nbar_count[id] = 0; s.nbar_gen[id]++; }
     else while (s.nbar_gen[id] == g) yield_now();
 }
+/* bar.arrive id, count: count this fiber in and go on */
+inline void named_arrive(int id, int count)
+{
+    State &s = S();
+    if (++s.nbar_count[id] == count) { s.nbar_count[id] = 0; s.nbar_gen[id]++; }
+}
 /* run one block */
 inline void run_block(const std::function<void()> &body)
 {
